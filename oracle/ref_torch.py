@@ -1,0 +1,132 @@
+"""CPU port of the reference path built from the SAME library calls the reference makes
+(``torch.stft``, ``F.conv1d``, ``F.batch_norm`` ... on CPU, all host threads).  TEST/BENCH
+INFRASTRUCTURE ONLY -- used by ``bench.py`` for the ``cpu_baseline`` leg and ``--impl reference``
+(the reference is pure Python over PyTorch and cannot travel to the GPU box), and by
+tests/test_oracle_golden.py as a second checker.  Never imported by the product package.
+
+Parity status: PINNED against tests/golden/*.npz (tests/test_oracle_golden.py::test_torch_port_*).
+Citations are file:line under /root/reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ref_numpy as R
+
+
+def features(audio: torch.Tensor, lengths: torch.Tensor, nfilt: int = 64, n_fft: int = 512, hop: int = 160,
+             win: int = 320, preemph: float = 0.97, fb: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """src/thunder/quartznet/transform.py:136-144,186-208,243-255,77-92 (eval mode)."""
+    x = torch.cat((audio[:, :1], audio[:, 1:] - preemph * audio[:, :-1]), dim=1)
+    window = torch.hann_window(win, periodic=False)
+    spec = torch.stft(x, n_fft=n_fft, hop_length=hop, win_length=win, center=True, window=window,
+                      return_complex=True)
+    spec = torch.view_as_real(spec)
+    p = torch.sqrt(spec.pow(2).sum(-1)).pow(2.0)
+    if fb is None:
+        fb = torch.from_numpy(R.mel_filterbank(1 + n_fft // 2, nfilt, 16000))
+    mel = torch.log(torch.matmul(fb.unsqueeze(0), p) + 2 ** -24)
+    seq = (torch.floor(lengths / hop) + 1).to(torch.long)
+    mask = (torch.arange(mel.shape[-1]).expand(mel.shape[0], -1) < seq.unsqueeze(1)).unsqueeze(1)
+    xm = mel.masked_fill(~mask, 0.0)
+    n = mask.sum(-1, keepdim=True)
+    mean = xm.sum(-1, keepdim=True) / n
+    std = ((xm - mean).pow(2).sum(-1, keepdim=True) / n).sqrt()
+    return ((xm - mean) / (std + 1e-5)).masked_fill(~mask, 0.0), seq
+
+
+def _mask(x, lengths):
+    m = torch.arange(x.shape[-1]).expand(x.shape[0], -1) < lengths.to(torch.long).unsqueeze(1)
+    return x.masked_fill(~m.unsqueeze(1), 0)
+
+
+def _bn(st, p, x):
+    return F.batch_norm(x, st[p + ".running_mean"], st[p + ".running_var"], st[p + ".weight"], st[p + ".bias"],
+                        False, 0.1, 1e-3)
+
+
+def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str):
+    """quartznet/blocks.py:317-338 / citrinet/blocks.py:177-197 (eval)."""
+    out, out_len = x, lengths
+    strides = cfg.sub_strides()
+    for r in range(cfg.repeat):
+        i = cfg.mconv_index(r)
+        s = strides[r]
+        pad = R.get_same_padding(cfg.kernel_size, s, cfg.dilation)
+        k = cfg.kernel_size
+        if cfg.separable:
+            out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i}.conv.weight"], None, s, pad, cfg.dilation,
+                           groups=out.shape[1])
+            out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
+            out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i + 1}.conv.weight"])
+            out = _bn(st, f"{prefix}mconv.{i + 2}.layer.0", out)
+        else:
+            out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i}.conv.weight"], None, s, pad, cfg.dilation)
+            out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
+            out = _bn(st, f"{prefix}mconv.{i + 1}.layer.0", out)
+        if r != cfg.repeat - 1:
+            out = F.relu(out)
+    if cfg.kind == "citrinet":
+        i_se = cfg.mconv_index(cfg.repeat - 1) + (3 if cfg.separable else 2)
+        y = out.mean(-1)
+        y = F.relu(y @ st[f"{prefix}mconv.{i_se}.layer.0.fc.0.weight"].T) @ st[f"{prefix}mconv.{i_se}.layer.0.fc.2.weight"].T
+        out = out * torch.sigmoid(y).unsqueeze(-1)
+    if cfg.residual:
+        res = F.conv1d(_mask(x, lengths), st[f"{prefix}res.0.conv.weight"], None, cfg.residual_stride())
+        out = out + _bn(st, f"{prefix}res.1.layer.0", res)
+    return F.relu(out), out_len
+
+
+def encoder(x, lengths, cfgs: List[R.BlockCfg], st):
+    for bi, cfg in enumerate(cfgs):
+        x, lengths = block(x, lengths, cfg, st, f"{bi}.")
+    return x, lengths
+
+
+def predict_ids(audio: torch.Tensor, cfgs, st, dec_w, dec_b, nfilt: int):
+    """module.py:88-100 up to the argmax; the string part is oracle.ref_numpy.decode_prediction."""
+    lengths = torch.full((audio.shape[0],), audio.shape[1], dtype=torch.long)
+    f, fl = features(audio, lengths, nfilt=nfilt)
+    e, el = encoder(f, fl, cfgs, st)
+    logits = F.conv1d(e, dec_w, dec_b)
+    return logits.argmax(1), logits, el
+
+
+def to_torch(state: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}
+
+
+def make_workload(name: str, batch: int, samples: int, nfilt: int):
+    """Closure running one step of a bench workload on CPU + a description of the bounded sample."""
+    from thunder_speech_b200 import synth
+
+    torch.set_grad_enabled(False)
+    x = torch.from_numpy(synth.audio(batch, samples, 1234, "noise"))
+    lens = torch.full((batch,), samples, dtype=torch.long)
+    if name == "features":
+        fb = torch.from_numpy(R.mel_filterbank(257, nfilt, 16000))
+        return (lambda: features(x, lens, nfilt=nfilt, fb=fb)), f"B={batch} x {samples / 16000:.0f} s, torch CPU fp32"
+    if name == "quartznet15x5":
+        cfgs = R.quartznet_cfgs(repeat_blocks=3)
+        st = to_torch(synth.encoder_state(synth.quartznet_block_list(repeat_blocks=3), seed=0))
+        dec = to_torch(synth.decoder_state(1024, 29, seed=1))
+        vocab = R.Vocab(synth.quartznet_vocab())
+    elif name == "citrinet1024":
+        c = synth.CITRINET_1024
+        cfgs = R.citrinet_cfgs(c["filters"], c["kernel_sizes"], c["strides"], feat_in=80)
+        st = to_torch(synth.encoder_state(synth.citrinet_block_list(c["filters"], c["kernel_sizes"], c["strides"], 80),
+                                          seed=0, se=True))
+        dec = to_torch(synth.decoder_state(640, 1025, seed=1))
+        vocab = R.Vocab(synth.citrinet_vocab(1024))
+    else:
+        raise ValueError(name)
+
+    def step():
+        ids, _, _ = predict_ids(x, cfgs, st, dec["weight"], dec["bias"], nfilt)
+        return R.decode_prediction(ids.numpy(), vocab)
+
+    return step, f"B={batch} x {samples / 16000:.0f} s predict() incl. greedy decode, torch CPU fp32"

@@ -1,0 +1,72 @@
+"""ctypes binding of ``libthunder_b200.so`` (the C ABI declared in ``include/thunder_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C thunder_speech_b200/csrc``).
+There is NO fallback: if the shared object is missing or a call fails, a ``RuntimeError`` /
+``ValueError`` is raised -- the product path never routes around the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libthunder_b200.so")
+
+TS_OK = 0
+TS_ERR_INVALID = -1
+TS_ERR_UNSUPPORTED = -2
+TS_ERR_NO_DEVICE = -3
+TS_F32 = 0
+TS_BF16 = 1
+
+_lib = None
+
+# name -> (restype, argtypes); kept in one table so the CPU test-suite can check that every symbol the
+# header declares is bound and exported.
+SIGNATURES = {
+    "ts_version": (c_char_p, []),
+    "ts_last_error": (c_char_p, []),
+    "ts_launch_count": (c_int64, []),
+    "ts_row_pitch": (c_int, [c_int]),
+    "ts_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ts_feature_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
+                                     c_int, c_void_p, c_void_p]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C thunder_speech_b200/csrc). thunder_speech_b200 has no CPU or eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a C-ABI return code into the exception the reference would raise for the same misuse."""
+    if rc == TS_OK:
+        return
+    msg = lib().ts_last_error().decode("utf-8", "replace")
+    if rc == TS_ERR_INVALID:
+        raise ValueError(f"{what}: {msg}")
+    if rc == TS_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: rc={rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().ts_launch_count())
+
+
+def row_pitch(T: int) -> int:
+    return int(lib().ts_row_pitch(int(T)))

@@ -1,0 +1,24 @@
+// Library-level entry points of libthunder_b200.so (version, errors, launch accounting).
+#include "ts_common.cuh"
+
+#include <atomic>
+
+namespace ts {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace ts
+
+extern "C" const char* ts_version(void) { return "thunder_b200 0.1 (sm_100a)"; }
+extern "C" const char* ts_last_error(void) { return ts::g_err; }
+extern "C" int64_t ts_launch_count(void) { return ts::g_launches.load(std::memory_order_relaxed); }
+extern "C" int ts_row_pitch(int T) { return T <= 0 ? 0 : ts::round_up(T, ts::kRowPitchAlign); }

@@ -1,0 +1,64 @@
+// Shared host/device helpers for libthunder_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/thunder_b200.h"
+
+namespace ts {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define TS_REQUIRE(cond, code, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::ts::set_error(__VA_ARGS__);            \
+      return (code);                           \
+    }                                          \
+  } while (0)
+
+#define TS_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::ts::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                        \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+// after a kernel launch: pick up launch-configuration errors without synchronising
+#define TS_LAUNCH_CHECK(name)                                                      \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      ::ts::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+      return (int)_e;                                                              \
+    }                                                                              \
+    ::ts::count_launch();                                                          \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+constexpr int kRowPitchAlign = 64;  // frames; 128 bytes of bf16
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ts
