@@ -289,7 +289,9 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
       const float d = (t < n) ? (v[j] - mean) : 0.f;
       ss += (double)d * (double)d;
     }
-    ss = warp_sum(ss);
+    // the reference subtracts the mean from the zero-FILLED tensor (blocks.py:141-145): each of the F - n masked
+    // frames contributes mean^2 to the numerator
+    ss = warp_sum(ss) + (double)(F - n) * (double)mean * (double)mean;
     const float stdv = (float)sqrt(ss / (double)n);
     const float den = stdv + div_guard;
 #pragma unroll
@@ -307,7 +309,7 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
       const float d = in[t] - mean;
       ss += (double)d * (double)d;
     }
-    ss = warp_sum(ss);
+    ss = warp_sum(ss) + (double)(F - n) * (double)mean * (double)mean;
     const float den = (float)sqrt(ss / (double)n) + div_guard;
     for (int t = lane; t < out_pitch; t += 32) store_out(o + t, (t < n) ? (in[t] - mean) / den : 0.f);
   }
