@@ -72,6 +72,55 @@ int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int
                          float div_guard, void* out, int out_dtype, int out_pitch,
                          int64_t* seq_len_out, void* stream);
 
+/* ---- (2) masked depthwise conv1d ----------------------------------------------------------- */
+/* Replaces MaskedConv1d.forward with groups == channels (src/thunder/quartznet/blocks.py:158-182; built by
+ * _get_conv_bn_layer, quartznet/blocks.py:195-201): zero frames t >= len_in[b], depthwise FIR, and zero
+ * output frames t' >= get_seq_len(len_in[b]) (the mask the following pointwise MaskedConv1d applies).
+ *   x  bf16 rows [B, C, pitch_in] holding T_in frames     w  [C, K] f32     len_in [B] i32 or NULL (= all valid)
+ *   y  bf16 rows [B, C, pitch_out], T_out = floor((T_in + 2P - D(K-1) - 1)/S) + 1
+ * TS_ERR_INVALID when both S > 1 and D > 1 (get_same_padding raises ValueError, src/thunder/blocks.py:192-193). */
+int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float* w, int K, int S, int D, int P,
+               const int32_t* len_in, void* y, int pitch_out, void* stream);
+
+/* ---- (3) pointwise conv / residual / decoder GEMM (tcgen05 + TMEM + TMA) ------------------- */
+/* out[b, m, t] = epi( W0[m, :] . X0[b, :, t] + W1[m, :] . X1[b, :, t] + shift[m] )
+ * Replaces the 1x1 MaskedConv1d + Masked(BatchNorm1d) + ReLU of a sub-block (quartznet/blocks.py:202-228), the
+ * residual branch `out + BN(conv1x1(x))` and `mout` ReLU of QuartznetBlock.forward (quartznet/blocks.py:329-337)
+ * when segment 1 is given, and conv1d_decoder (src/thunder/blocks.py:199-216) with out_dtype = TS_F32.
+ * Eval BatchNorm scales must be folded into the bf16 weights by the caller; `shift` is the sum of BN shifts / bias.
+ *   w0 [Cout, cin0] bf16, x0 bf16 rows [B, cin0, x0_pitch]; segment 1 likewise or NULL/0
+ *   lens [B] i32 or NULL: frames t >= lens[b] are stored as zero (input mask of the next MaskedConv1d)
+ *   out  bf16 rows [B, Cout, out_pitch] (pitch % 64 == 0) or f32 [B, Cout, out_pitch]
+ * SqueezeExcite (citrinet/blocks.py:70-83): `pool` [B, Cout] f32 accumulates sum_t (acc + shift) over t < T
+ * (atomicAdd; caller zeroes it); `se_scale` [B, Cout] + `y1` bf16 rows: out = epi(acc + shift + se_scale * y1). */
+int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
+               int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
+               int out_dtype, int out_pitch, int relu, float* pool, const float* se_scale, const void* y1,
+               int y1_pitch, void* stream);
+
+/* ---- (4) SqueezeExcite FC, greedy CTC ------------------------------------------------------- */
+/* gate[b, :] = sigmoid(W2 relu(W1 (pool[b, :] / T)))  -- SqueezeExcite.fc + sigmoid (citrinet/blocks.py:63-83).
+ *   pool [B, C] f32 sums over all T frames, w1 [H, C] f32, w2 [C, H] f32 (nn.Linear layouts, no bias) */
+int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* gate,
+             void* stream);
+
+/* Greedy CTC: `pred.argmax(1)` (src/thunder/module.py:100; first maximal index, NaN maximal) followed by the
+ * per-row torch.unique_consecutive of decode_prediction (src/thunder/text_processing/transform.py:107-110).
+ *   logits [B, V, pitch] f32 or bf16 rows, T valid frames
+ *   ids [B, T] i64 argmax (may be NULL); collapsed [B, T] i64 padded with -1; counts [B] i32
+ *   drop_blank < 0 keeps blanks (the reference removes the blank token as a string, vocab.py:114-130) */
+int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch, int64_t* ids, int64_t* collapsed,
+                  int32_t* counts, int drop_blank, void* stream);
+
+/* ---- layout / length plumbing at module boundaries ------------------------------------------ */
+/* contiguous [B, C, T] (TS_F32 or TS_BF16) -> bf16 rows [B, C, pitch] (frames >= T zero) and back to f32 */
+int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, void* out, int pitch, void* stream);
+int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, void* stream);
+/* MaskedConv1d.get_seq_len (quartznet/blocks.py:142-156) on i32 lengths; i64 <-> i32 conversions */
+int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D, int P, void* stream);
+int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream);
+int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

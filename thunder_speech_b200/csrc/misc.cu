@@ -1,0 +1,218 @@
+// Small kernels around the two hot ones: layout conversion at module boundaries, per-layer length
+// bookkeeping, the SqueezeExcite FC micro-kernel and the greedy CTC argmax + collapse.
+#include "ts_common.cuh"
+
+namespace ts {
+namespace misc {
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// [B, C, T] (contiguous, f32 or bf16) -> bf16 rows [B, C, pitch]; frames t >= T are zero-filled.
+template <typename InT>
+__global__ void pack_rows_kernel(const InT* __restrict__ in, int T, __nv_bfloat16* __restrict__ out, int pitch,
+                                 long long rows) {
+  const long long row = blockIdx.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= rows || t >= pitch) return;
+  const float v = (t < T) ? ld_as_float(in + row * T + t) : 0.f;
+  out[row * pitch + t] = __float2bfloat16_rn(v);
+}
+
+// bf16 rows [B, C, pitch] -> contiguous f32 [B, C, T]
+__global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ in, int pitch, float* __restrict__ out, int T,
+                                   long long rows) {
+  const long long row = blockIdx.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= rows || t >= T) return;
+  out[row * T + t] = __bfloat162float(in[row * pitch + t]);
+}
+
+// out[b] = clamp-free MaskedConv1d.get_seq_len (quartznet/blocks.py:142-156): floor((L + 2p - d(k-1) - 1)/s) + 1
+__global__ void conv_lengths_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int B, int K, int S,
+                                    int D, int P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int num = in[b] + 2 * P - D * (K - 1) - 1;
+  int q = num / S;
+  if (num % S != 0 && num < 0) --q;
+  out[b] = q + 1;
+}
+
+__global__ void lengths_i64_to_i32_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int64_t v = in[b];
+  v = v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v);
+  out[b] = (int32_t)v;
+}
+__global__ void lengths_i32_to_i64_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = in[b];
+}
+
+// SqueezeExcite excitation (citrinet/blocks.py:77-83): gate[b, c] = sigmoid(W2 relu(W1 (pool[b, :] / T))).
+// One CTA per batch element; pool holds the per-channel SUMS over all T frames (no mask -- the reference pools
+// with AdaptiveAvgPool1d over the whole padded time axis).
+__global__ void __launch_bounds__(256)
+se_fc_kernel(const float* __restrict__ pool, float inv_T, const float* __restrict__ w1, const float* __restrict__ w2,
+             int C, int H, float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  float* mean = sm;        // [C]
+  float* hid = sm + C;     // [H]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(size_t)b * C + c] * inv_T;
+  __syncthreads();
+  for (int h = warp; h < H; h += blockDim.x / 32) {
+    const float* wr = w1 + (size_t)h * C;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(wr[c], mean[c], a);
+    a = warp_sum(a);
+    if (lane == 0) hid[h] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += blockDim.x / 32) {
+    const float* wr = w2 + (size_t)c * H;
+    float a = 0.f;
+    for (int h = lane; h < H; h += 32) a = fmaf(wr[h], hid[h], a);
+    a = warp_sum(a);
+    if (lane == 0) gate[(size_t)b * C + c] = 1.f / (1.f + __expf(-a));
+  }
+}
+
+// Greedy CTC decode (module.py:100 `pred.argmax(1)`; text_processing/transform.py:107-110 unique_consecutive).
+// One CTA per utterance.  Phase 1: argmax over the vocabulary axis of logits[b, :, t] (first maximal index wins,
+// NaN counts as maximal -- torch.argmax semantics).  Phase 2: warp 0 collapses consecutive repeats with ballot
+// + popcount prefix sums.  Blanks are kept (the reference strips the blank *string* after joining) unless
+// drop_blank >= 0.
+template <typename InT>
+__global__ void __launch_bounds__(256)
+ctc_greedy_kernel(const InT* __restrict__ logits, int V, int T, int pitch, int64_t* __restrict__ ids,
+                  int64_t* __restrict__ collapsed, int32_t* __restrict__ counts, int drop_blank) {
+  extern __shared__ int s_ids[];
+  const int b = blockIdx.x;
+  const InT* base = logits + (size_t)b * V * pitch;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float best = ld_as_float(base + t);
+    int bi = 0;
+    bool best_nan = best != best;
+    for (int v = 1; v < V && !best_nan; ++v) {
+      const float x = ld_as_float(base + (size_t)v * pitch + t);
+      if (x != x) {
+        bi = v;
+        best_nan = true;
+      } else if (x > best) {
+        best = x;
+        bi = v;
+      }
+    }
+    s_ids[t] = bi;
+    if (ids != nullptr) ids[(size_t)b * T + t] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int n = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      int id = -1;
+      if (t < T) {
+        id = s_ids[t];
+        keep = (t == 0) || (id != s_ids[t - 1]);
+        if (drop_blank >= 0 && id == drop_blank) keep = false;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) collapsed[(size_t)b * T + n + __popc(m & ((1u << lane) - 1u))] = id;
+      n += __popc(m);
+    }
+    for (int t = n + lane; t < T; t += 32) collapsed[(size_t)b * T + t] = -1;
+    if (lane == 0) counts[b] = n;
+  }
+}
+
+}  // namespace misc
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, void* out, int pitch, void* stream) {
+  TS_REQUIRE(in && out, TS_ERR_INVALID, "ts_pack_rows: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_pack_rows: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_pack_rows: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch, 256));
+  if (in_dtype == TS_F32)
+    misc::pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, T, (__nv_bfloat16*)out, pitch, rows);
+  else
+    misc::pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, T,
+                                                                                  (__nv_bfloat16*)out, pitch, rows);
+  TS_LAUNCH_CHECK("pack_rows_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, void* stream) {
+  TS_REQUIRE(in && out, TS_ERR_INVALID, "ts_unpack_rows: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_unpack_rows: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_unpack_rows: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(T, 256));
+  misc::unpack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, pitch, out, T, rows);
+  TS_LAUNCH_CHECK("unpack_rows_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D, int P, void* stream) {
+  TS_REQUIRE(in && out && B > 0 && K > 0 && S > 0 && D > 0 && P >= 0, TS_ERR_INVALID, "ts_conv_lengths: bad arguments");
+  misc::conv_lengths_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(in, out, B, K, S, D, P);
+  TS_LAUNCH_CHECK("conv_lengths_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream) {
+  TS_REQUIRE(in && out && B > 0, TS_ERR_INVALID, "ts_lengths_to_i32: bad arguments");
+  misc::lengths_i64_to_i32_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(in, out, B);
+  TS_LAUNCH_CHECK("lengths_i64_to_i32_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* stream) {
+  TS_REQUIRE(in && out && B > 0, TS_ERR_INVALID, "ts_lengths_to_i64: bad arguments");
+  misc::lengths_i32_to_i64_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(in, out, B);
+  TS_LAUNCH_CHECK("lengths_i32_to_i64_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* gate,
+                        void* stream) {
+  TS_REQUIRE(pool && w1 && w2 && gate, TS_ERR_INVALID, "ts_se_fc: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && H > 0 && T > 0, TS_ERR_INVALID, "ts_se_fc: bad sizes");
+  const size_t smem = (size_t)(C + H) * sizeof(float);
+  TS_REQUIRE(smem <= 48 * 1024, TS_ERR_UNSUPPORTED, "ts_se_fc: C=%d too large", C);
+  misc::se_fc_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, w2, C, H, gate);
+  TS_LAUNCH_CHECK("se_fc_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch, int64_t* ids,
+                             int64_t* collapsed, int32_t* counts, int drop_blank, void* stream) {
+  TS_REQUIRE(logits && collapsed && counts, TS_ERR_INVALID, "ts_ctc_greedy: null pointer");
+  TS_REQUIRE(B > 0 && V > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_ctc_greedy: bad sizes");
+  const size_t smem = (size_t)T * sizeof(int);
+  TS_REQUIRE(smem <= 200 * 1024, TS_ERR_UNSUPPORTED, "ts_ctc_greedy: T=%d too long for one CTA", T);
+  if (dtype == TS_F32) {
+    auto k = misc::ctc_greedy_kernel<float>;
+    if (smem > 48 * 1024) TS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, 256, smem, (cudaStream_t)stream>>>((const float*)logits, V, T, pitch, ids, collapsed, counts, drop_blank);
+  } else if (dtype == TS_BF16) {
+    auto k = misc::ctc_greedy_kernel<__nv_bfloat16>;
+    if (smem > 48 * 1024) TS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, V, T, pitch, ids, collapsed, counts,
+                                              drop_blank);
+  } else {
+    TS_REQUIRE(false, TS_ERR_INVALID, "ts_ctc_greedy: bad dtype %d", dtype);
+  }
+  TS_LAUNCH_CHECK("ctc_greedy_kernel");
+  return TS_OK;
+}

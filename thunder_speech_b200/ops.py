@@ -8,7 +8,7 @@ there is no CPU fallback.  Fake (meta) implementations give shapes to ``torch.ji
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -79,3 +79,149 @@ def _(audio, lengths, window_full, twiddle, mel_start, mel_count, mel_off, mel_w
     else:
         out = audio.new_empty((B, nfilt, F), dtype=torch.float32)
     return out, audio.new_empty((B,), dtype=torch.int64)
+
+
+# ------------------------------------------------------------------------------------------- layout
+def row_pitch(T: int) -> int:
+    """Pitch (frames) of a padded bf16 activation row holding T frames (multiple of 64)."""
+    return (int(T) + 63) // 64 * 64
+
+
+@torch.library.custom_op(f"{NS}::pack_rows", mutates_args=())
+def pack_rows(x: Tensor) -> Tensor:
+    """``[B, C, T]`` (f32 / bf16, contiguous) -> bf16 padded rows ``[B, C, row_pitch(T)]``, pad frames zero."""
+    _need_cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B, C, T = x.shape
+    out = torch.empty((B, C, row_pitch(T)), device=x.device, dtype=torch.bfloat16)
+    dt = _lib.TS_F32 if x.dtype == torch.float32 else _lib.TS_BF16
+    _lib.check(_lib.lib().ts_pack_rows(_ptr(x), dt, B, C, T, _ptr(out), out.shape[2], _stream()), "ts_pack_rows")
+    return out
+
+
+@pack_rows.register_fake
+def _(x):
+    B, C, T = x.shape
+    return x.new_empty((B, C, row_pitch(T)), dtype=torch.bfloat16)
+
+
+@torch.library.custom_op(f"{NS}::unpack_rows", mutates_args=())
+def unpack_rows(x: Tensor, T: int) -> Tensor:
+    """bf16 padded rows ``[B, C, pitch]`` -> contiguous f32 ``[B, C, T]``."""
+    _need_cuda(x)
+    B, C, pitch = x.shape
+    out = torch.empty((B, C, T), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ts_unpack_rows(_ptr(x), pitch, B, C, T, _ptr(out), _stream()), "ts_unpack_rows")
+    return out
+
+
+@unpack_rows.register_fake
+def _(x, T):
+    return x.new_empty((x.shape[0], x.shape[1], T), dtype=torch.float32)
+
+
+def lengths_i32(lengths: Tensor) -> Tensor:
+    """Any numeric lengths tensor -> int32 device tensor (``.type(torch.long)`` truncation first, like
+    ``lengths_to_mask``, src/thunder/blocks.py:166)."""
+    return lengths.to(torch.int64).to(torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------- depthwise
+@torch.library.custom_op(f"{NS}::dw_conv", mutates_args=())
+def dw_conv(x: Tensor, T_in: int, weight: Tensor, stride: int, dilation: int, padding: int,
+            lens: Optional[Tensor]) -> Tensor:
+    """Masked depthwise conv over bf16 rows.  ``weight`` is ``[C, K]`` f32; ``lens`` i32 ``[B]`` input lengths."""
+    _need_cuda(x, weight)
+    B, C, pitch = x.shape
+    K = weight.shape[1]
+    T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
+    out = torch.empty((B, C, row_pitch(max(T_out, 1))), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ts_dw_conv(_ptr(x), B, C, T_in, pitch, _ptr(weight), K, stride, dilation, padding,
+                                     _ptr(lens) if lens is not None else None, _ptr(out), out.shape[2], _stream()),
+               "ts_dw_conv")
+    return out
+
+
+@dw_conv.register_fake
+def _(x, T_in, weight, stride, dilation, padding, lens):
+    K = weight.shape[1]
+    T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
+    return x.new_empty((x.shape[0], x.shape[1], row_pitch(max(T_out, 1))))
+
+
+# ------------------------------------------------------------------------------------------- pointwise
+@torch.library.custom_op(f"{NS}::pw_gemm", mutates_args=("pool",))
+def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], T: int, shift: Optional[Tensor],
+            lens: Optional[Tensor], out_f32: bool, relu: bool, pool: Optional[Tensor], se_scale: Optional[Tensor],
+            y1: Optional[Tensor]) -> Tensor:
+    """tcgen05 pointwise GEMM with fused BN-shift / residual segment / ReLU / tail mask / SE epilogues.
+    ``w*`` bf16 ``[Cout, Cin]`` (BN scale folded in), ``x*`` bf16 rows ``[B, Cin, pitch]``."""
+    _need_cuda(w0, x0)
+    B, cin0, p0 = x0.shape
+    Cout = w0.shape[0]
+    if out_f32:
+        out = torch.empty((B, Cout, T), device=x0.device, dtype=torch.float32)
+        dt, pitch = _lib.TS_F32, T
+    else:
+        out = torch.empty((B, Cout, row_pitch(T)), device=x0.device, dtype=torch.bfloat16)
+        dt, pitch = _lib.TS_BF16, out.shape[2]
+    cin1 = x1.shape[1] if x1 is not None else 0
+    p1 = x1.shape[2] if x1 is not None else 0
+
+    def P(t):
+        return _ptr(t) if t is not None else None
+
+    _lib.check(_lib.lib().ts_pw_gemm(_ptr(w0), _ptr(x0), cin0, p0, P(w1), P(x1), cin1, p1, B, Cout, T, P(shift),
+                                     P(lens), _ptr(out), dt, pitch, int(relu), P(pool), P(se_scale), P(y1),
+                                     y1.shape[2] if y1 is not None else 0, _stream()), "ts_pw_gemm")
+    return out
+
+
+@pw_gemm.register_fake
+def _(w0, x0, w1, x1, T, shift, lens, out_f32, relu, pool, se_scale, y1):
+    B, Cout = x0.shape[0], w0.shape[0]
+    if out_f32:
+        return x0.new_empty((B, Cout, T), dtype=torch.float32)
+    return x0.new_empty((B, Cout, row_pitch(T)))
+
+
+# ------------------------------------------------------------------------------------------- SE / CTC
+@torch.library.custom_op(f"{NS}::se_fc", mutates_args=())
+def se_fc(pool: Tensor, T: int, w1: Tensor, w2: Tensor) -> Tensor:
+    """``sigmoid(W2 relu(W1 pool/T))`` -> gate ``[B, C]`` f32 (citrinet/blocks.py:63-83)."""
+    _need_cuda(pool, w1, w2)
+    B, C = pool.shape
+    gate = torch.empty_like(pool)
+    _lib.check(_lib.lib().ts_se_fc(_ptr(pool), B, C, w1.shape[0], T, _ptr(w1), _ptr(w2), _ptr(gate), _stream()),
+               "ts_se_fc")
+    return gate
+
+
+@se_fc.register_fake
+def _(pool, T, w1, w2):
+    return torch.empty_like(pool)
+
+
+@torch.library.custom_op(f"{NS}::ctc_greedy", mutates_args=())
+def ctc_greedy(logits: Tensor, T: int, drop_blank: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """``argmax(1)`` + per-row ``unique_consecutive``.  ``logits`` is f32 ``[B, V, T]`` or bf16 rows
+    ``[B, V, pitch]``.  Returns ``(ids[B,T] i64, collapsed[B,T] i64 padded with -1, counts[B] i32)``."""
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    B, V, pitch = logits.shape
+    dt = _lib.TS_F32 if logits.dtype == torch.float32 else _lib.TS_BF16
+    ids = torch.empty((B, T), device=logits.device, dtype=torch.int64)
+    col = torch.empty((B, T), device=logits.device, dtype=torch.int64)
+    cnt = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    _lib.check(_lib.lib().ts_ctc_greedy(_ptr(logits), dt, B, V, T, pitch, _ptr(ids), _ptr(col), _ptr(cnt),
+                                        drop_blank, _stream()), "ts_ctc_greedy")
+    return ids, col, cnt
+
+
+@ctc_greedy.register_fake
+def _(logits, T, drop_blank):
+    B = logits.shape[0]
+    return (logits.new_empty((B, T), dtype=torch.int64), logits.new_empty((B, T), dtype=torch.int64),
+            logits.new_empty((B,), dtype=torch.int32))
