@@ -104,6 +104,11 @@ int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const voi
 int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* gate,
              void* stream);
 
+/* out = relu(gate[b, c] * y1[b, c, t]) over bf16 rows: SqueezeExcite scale + `mout` ReLU for blocks without a
+ * residual branch (citrinet/blocks.py:154,195-197); frames t >= lens[b] are stored as zero when lens != NULL */
+int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int relu,
+                void* out, void* stream);
+
 /* Greedy CTC: `pred.argmax(1)` (src/thunder/module.py:100; first maximal index, NaN maximal) followed by the
  * per-row torch.unique_consecutive of decode_prediction (src/thunder/text_processing/transform.py:107-110).
  *   logits [B, V, pitch] f32 or bf16 rows, T valid frames
@@ -113,8 +118,10 @@ int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch,
                   int32_t* counts, int drop_blank, void* stream);
 
 /* ---- layout / length plumbing at module boundaries ------------------------------------------ */
-/* contiguous [B, C, T] (TS_F32 or TS_BF16) -> bf16 rows [B, C, pitch] (frames >= T zero) and back to f32 */
-int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, void* out, int pitch, void* stream);
+/* contiguous [B, C, T] (TS_F32 or TS_BF16) -> bf16 rows [B, C, pitch] (frames >= min(T, lens[b]) zero; lens may
+ * be NULL) -- the MaskedConv1d.mask_fill of the first consumer (quartznet/blocks.py:158-167) -- and back to f32 */
+int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, const int32_t* lens, void* out, int pitch,
+                 void* stream);
 int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, void* stream);
 /* MaskedConv1d.get_seq_len (quartznet/blocks.py:142-156) on i32 lengths; i64 <-> i32 conversions */
 int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D, int P, void* stream);

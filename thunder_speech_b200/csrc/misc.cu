@@ -8,14 +8,16 @@ namespace misc {
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-// [B, C, T] (contiguous, f32 or bf16) -> bf16 rows [B, C, pitch]; frames t >= T are zero-filled.
+// [B, C, T] (contiguous, f32 or bf16) -> bf16 rows [B, C, pitch]; frames t >= min(T, lens[b]) are zero-filled.
 template <typename InT>
 __global__ void pack_rows_kernel(const InT* __restrict__ in, int T, __nv_bfloat16* __restrict__ out, int pitch,
-                                 long long rows) {
+                                 long long rows, int C, const int32_t* __restrict__ lens) {
   const long long row = blockIdx.x;
   const int t = blockIdx.y * blockDim.x + threadIdx.x;
   if (row >= rows || t >= pitch) return;
-  const float v = (t < T) ? ld_as_float(in + row * T + t) : 0.f;
+  int lim = T;
+  if (lens != nullptr) lim = min(lim, lens[row / C]);  // MaskedConv1d.mask_fill of the consumer (quartznet/blocks.py:158-167)
+  const float v = (t < lim) ? ld_as_float(in + row * T + t) : 0.f;
   out[row * pitch + t] = __float2bfloat16_rn(v);
 }
 
@@ -81,6 +83,32 @@ se_fc_kernel(const float* __restrict__ pool, float inv_T, const float* __restric
   }
 }
 
+
+// SE excite for blocks WITHOUT a residual branch (Citrinet stem / epilogue, citrinet/blocks.py:154,195-197):
+// out = relu(gate[b, c] * y1[b, c, t]), frames t >= lens[b] stored as zero when lens is given.  8 frames per thread.
+__global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ y1, const float* __restrict__ gate, int C, int pitch,
+                                const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ out,
+                                long long rows) {
+  const long long row = blockIdx.x;
+  const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t >= pitch) return;
+  const float g = gate[row];
+  const int lim = lens ? lens[row / C] : pitch;
+  const uint4 u = *reinterpret_cast<const uint4*>(y1 + row * pitch + t);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float lo = g * __uint_as_float(w[h] << 16), hi = g * __uint_as_float(w[h] & 0xFFFF0000u);
+    if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+    if (t + 2 * h >= lim) lo = 0.f;
+    if (t + 2 * h + 1 >= lim) hi = 0.f;
+    __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
+    o[h] = *reinterpret_cast<uint32_t*>(&pr);
+  }
+  *reinterpret_cast<uint4*>(out + row * pitch + t) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // Greedy CTC decode (module.py:100 `pred.argmax(1)`; text_processing/transform.py:107-110 unique_consecutive).
 // One CTA per utterance.  Phase 1: argmax over the vocabulary axis of logits[b, :, t] (first maximal index wins,
 // NaN counts as maximal -- torch.argmax semantics).  Phase 2: warp 0 collapses consecutive repeats with ballot
@@ -137,17 +165,19 @@ ctc_greedy_kernel(const InT* __restrict__ logits, int V, int T, int pitch, int64
 
 using namespace ts;
 
-extern "C" int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, void* out, int pitch, void* stream) {
+extern "C" int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, const int32_t* lens, void* out,
+                            int pitch, void* stream) {
   TS_REQUIRE(in && out, TS_ERR_INVALID, "ts_pack_rows: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_pack_rows: bad sizes");
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_pack_rows: too many rows");
   dim3 grid((unsigned)rows, ceil_div(pitch, 256));
   if (in_dtype == TS_F32)
-    misc::pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, T, (__nv_bfloat16*)out, pitch, rows);
+    misc::pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, T, (__nv_bfloat16*)out, pitch, rows, C, lens);
   else
     misc::pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, T,
-                                                                                  (__nv_bfloat16*)out, pitch, rows);
+                                                                                  (__nv_bfloat16*)out, pitch, rows, C,
+                                                                                  lens);
   TS_LAUNCH_CHECK("pack_rows_kernel");
   return TS_OK;
 }
@@ -214,5 +244,18 @@ extern "C" int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T,
     TS_REQUIRE(false, TS_ERR_INVALID, "ts_ctc_greedy: bad dtype %d", dtype);
   }
   TS_LAUNCH_CHECK("ctc_greedy_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int relu,
+                           void* out, void* stream) {
+  TS_REQUIRE(y1 && gate && out, TS_ERR_INVALID, "ts_se_apply: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && pitch > 0 && pitch % 8 == 0, TS_ERR_INVALID, "ts_se_apply: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_se_apply: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
+  misc::se_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y1, gate, C, pitch, lens, relu,
+                                                                (__nv_bfloat16*)out, rows);
+  TS_LAUNCH_CHECK("se_apply_kernel");
   return TS_OK;
 }

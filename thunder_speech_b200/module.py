@@ -1,0 +1,126 @@
+"""``BaseCTCModule`` forward / predict (mirrors ``src/thunder/module.py:25-100``) without Lightning.
+
+    module = CTCModule(encoder, decoder, audio_transform, text_transform)
+    logits, out_lengths = module(audio, lengths)        # forward, module.py:74-86
+    texts = module.predict(audio)                       # module.py:88-100
+
+``forward`` keeps activations in the kernels' bf16 row layout from the feature kernel to the decoder GEMM and
+returns fp32 logits ``[B, V, T']`` like the reference.  ``predict`` adds the greedy CTC kernel and detokenises
+on the host after a single device-to-host copy.  Optimiser / metric / training-step plumbing of the reference
+class (module.py:102-189) is Lightning glue outside the forward hot path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+
+__all__ = ["CTCModule", "BaseCTCModule"]
+
+
+class CTCModule(nn.Module):
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, audio_transform: nn.Module,
+                 text_transform: nn.Module, encoder_final_dimension: Optional[int] = None):
+        super().__init__()
+        self.audio_transform = audio_transform
+        self.encoder = encoder
+        self.decoder = decoder
+        self.text_transform = text_transform
+        self.encoder_final_dimension = encoder_final_dimension
+        self._dec_cache = None
+        self._graphs: Dict[Tuple[int, int], "_PredictGraph"] = {}
+
+    # -- decoder parameters as GEMM operands ----------------------------------------------------
+    def _decoder_operands(self) -> Tuple[Tensor, Tensor]:
+        dec = self.decoder
+        if not isinstance(dec, nn.Conv1d) or dec.kernel_size[0] != 1:
+            raise NotImplementedError("only conv1d_decoder (1x1 Conv1d with bias) is implemented")
+        key = (dec.weight.data_ptr(), dec.weight._version, dec.bias.data_ptr(), dec.bias._version)
+        if self._dec_cache is None or self._dec_cache[0] != key:
+            w = dec.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
+            b = dec.bias.detach().float().contiguous()
+            self._dec_cache = (key, w, b)
+        return self._dec_cache[1], self._dec_cache[2]
+
+    def _logits_rows(self, x: Tensor, lengths: Tensor):
+        """audio -> (fp32 logits [B,V,T'], T', device i32 lengths, i64 feature lengths)."""
+        N = x.shape[-1]
+        hop = self.audio_transform[1].hop_length
+        F = 1 + N // hop
+        feats, feat_len = self.audio_transform.features(x, lengths, bf16_pitch=ops.row_pitch(F))
+        l32 = feat_len.to(torch.int32)
+        rows, T, l32 = self.encoder.forward_rows(feats, F, l32)
+        w, b = self._decoder_operands()
+        logits = ops.pw_gemm(w, rows, None, None, T, b, None, True, False, None, None, None)
+        return logits, T, l32, feat_len
+
+    def forward(self, x: Tensor, lengths: Tensor) -> Tuple[Tensor, Optional[Tensor]]:
+        """``(audio[B,N], lengths[B]) -> (logits[B,V,T'] f32, out_lengths[B] i64)`` (module.py:74-86)."""
+        if self.training:
+            raise NotImplementedError("inference path only: call .eval() (training step is SURVEY.md 8(f) row 1)")
+        with torch.no_grad():
+            logits, T, l32, _ = self._logits_rows(x, lengths)
+            return logits, l32.to(torch.int64)
+
+    @torch.no_grad()
+    def predict_ids(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """Device part of ``predict``: ``(argmax ids [B,T'], collapsed ids [B,T'] (-1 padded), counts [B])``."""
+        lengths = torch.full((x.shape[0],), x.shape[-1], device=x.device, dtype=torch.int64)  # module.py:98
+        logits, T, _, _ = self._logits_rows(x, lengths)
+        return ops.ctc_greedy(logits, T, -1)
+
+    @torch.no_grad()
+    def predict(self, x: Tensor) -> List[str]:
+        """Audio ``[batch, time]`` -> transcriptions (module.py:88-100): every frame is decoded, lengths = N."""
+        _, col, cnt = self.predict_ids(x)
+        return self.text_transform.decode_collapsed(col, cnt)
+
+    # -- CUDA-graph replay of predict_ids for a fixed (batch, samples) shape -----------------------
+    @torch.no_grad()
+    def predict_ids_graphed(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """Same result as :meth:`predict_ids`; the ~200 kernel launches of one forward are captured once per
+        input shape into a CUDA graph and replayed (launch-bound otherwise at small batch)."""
+        key = (x.shape[0], x.shape[1])
+        g = self._graphs.get(key)
+        if g is None:
+            g = _PredictGraph(self, x)
+            self._graphs[key] = g
+        return g.replay(x)
+
+    @torch.no_grad()
+    def predict_graphed(self, x: Tensor) -> List[str]:
+        _, col, cnt = self.predict_ids_graphed(x)
+        return self.text_transform.decode_collapsed(col, cnt)
+
+
+class _PredictGraph:
+    def __init__(self, module: CTCModule, example: Tensor):
+        from . import _lib
+
+        self.static_in = example.clone()
+        # warm-up on a side stream (sets kernel attributes, builds plans), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                module.predict_ids(self.static_in)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_out = module.predict_ids(self.static_in)
+        self.kernels_per_replay = _lib.launch_count() - n0
+        self.replays = 0
+
+    def replay(self, x: Tensor):
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.static_out
+
+
+BaseCTCModule = CTCModule

@@ -88,8 +88,9 @@ def row_pitch(T: int) -> int:
 
 
 @torch.library.custom_op(f"{NS}::pack_rows", mutates_args=())
-def pack_rows(x: Tensor) -> Tensor:
-    """``[B, C, T]`` (f32 / bf16, contiguous) -> bf16 padded rows ``[B, C, row_pitch(T)]``, pad frames zero."""
+def pack_rows(x: Tensor, lens: Optional[Tensor] = None) -> Tensor:
+    """``[B, C, T]`` (f32 / bf16, contiguous) -> bf16 padded rows ``[B, C, row_pitch(T)]``; pad frames and, when
+    ``lens`` (i32 ``[B]``) is given, frames ``t >= lens[b]`` are zero (``MaskedConv1d.mask_fill``)."""
     _need_cuda(x)
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
@@ -97,12 +98,13 @@ def pack_rows(x: Tensor) -> Tensor:
     B, C, T = x.shape
     out = torch.empty((B, C, row_pitch(T)), device=x.device, dtype=torch.bfloat16)
     dt = _lib.TS_F32 if x.dtype == torch.float32 else _lib.TS_BF16
-    _lib.check(_lib.lib().ts_pack_rows(_ptr(x), dt, B, C, T, _ptr(out), out.shape[2], _stream()), "ts_pack_rows")
+    _lib.check(_lib.lib().ts_pack_rows(_ptr(x), dt, B, C, T, _ptr(lens) if lens is not None else None, _ptr(out),
+                                       out.shape[2], _stream()), "ts_pack_rows")
     return out
 
 
 @pack_rows.register_fake
-def _(x):
+def _(x, lens=None):
     B, C, T = x.shape
     return x.new_empty((B, C, row_pitch(T)), dtype=torch.bfloat16)
 
@@ -225,3 +227,34 @@ def _(logits, T, drop_blank):
     B = logits.shape[0]
     return (logits.new_empty((B, T), dtype=torch.int64), logits.new_empty((B, T), dtype=torch.int64),
             logits.new_empty((B,), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{NS}::se_apply", mutates_args=())
+def se_apply(y1: Tensor, gate: Tensor, lens: Optional[Tensor], relu: bool) -> Tensor:
+    """``relu(gate[b,c] * y1)`` over bf16 rows (SE scale for blocks without a residual branch)."""
+    _need_cuda(y1, gate)
+    B, C, pitch = y1.shape
+    out = torch.empty_like(y1)
+    _lib.check(_lib.lib().ts_se_apply(_ptr(y1), _ptr(gate), B, C, pitch, _ptr(lens) if lens is not None else None,
+                                      int(relu), _ptr(out), _stream()), "ts_se_apply")
+    return out
+
+
+@se_apply.register_fake
+def _(y1, gate, lens, relu):
+    return torch.empty_like(y1)
+
+
+@torch.library.custom_op(f"{NS}::conv_lengths", mutates_args=())
+def conv_lengths(lens: Tensor, kernel_size: int, stride: int, dilation: int, padding: int) -> Tensor:
+    """``MaskedConv1d.get_seq_len`` (quartznet/blocks.py:142-156) on an i32 device tensor."""
+    _need_cuda(lens)
+    out = torch.empty_like(lens)
+    _lib.check(_lib.lib().ts_conv_lengths(_ptr(lens), _ptr(out), lens.numel(), kernel_size, stride, dilation,
+                                          padding, _stream()), "ts_conv_lengths")
+    return out
+
+
+@conv_lengths.register_fake
+def _(lens, kernel_size, stride, dilation, padding):
+    return torch.empty_like(lens)

@@ -1,0 +1,91 @@
+"""Greedy CTC detokenisation (the decode half of ``src/thunder/text_processing``).
+
+Only what ``BaseCTCModule.predict`` needs is here: the token table with the reference's special-token rules
+(``Vocabulary``, vocab.py:18-67,114-130) and ``BatchTextTransformer.decode_prediction``
+(transform.py:93-122).  Tokenisers / text encoding for training are host-side string processing outside the
+forward hot path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+__all__ = ["Vocabulary", "BatchTextTransformer"]
+
+
+class Vocabulary(nn.Module):
+    """Token table: special tokens are appended in the order blank, pad, unknown, start, end, skipping ``None``
+    and tokens already present (vocab.py:44-56).  ``blank_idx`` is therefore ``len(tokens)`` by default."""
+
+    def __init__(self, tokens: List[str], blank_token: str = "<blank>", pad_token: Optional[str] = None,
+                 unknown_token: Optional[str] = None, start_token: Optional[str] = None,
+                 end_token: Optional[str] = None):
+        super().__init__()
+        self.unknown_token = unknown_token
+        self.start_token = start_token
+        self.end_token = end_token
+        self.blank_token = blank_token
+        self.pad_token = pad_token or blank_token
+        itos = list(tokens)
+        for tok in (blank_token, pad_token, unknown_token, start_token, end_token):
+            if tok and tok not in itos:
+                itos.append(tok)
+        self.itos = itos
+        self.stoi = {t: i for i, t in enumerate(itos)}
+        self.blank_idx = itos.index(self.blank_token)
+        self.pad_idx = itos.index(self.pad_token)
+
+    def decode_into_text(self, indices) -> List[str]:
+        return [self.itos[int(i)] for i in indices]
+
+    def remove_special_tokens(self, text: str) -> str:
+        """String replacement in the reference's order (vocab.py:114-130)."""
+        text = text.replace(self.blank_token, "")
+        text = text.replace(self.pad_token, "")
+        if self.start_token is not None:
+            text = text.replace(self.start_token, "")
+        if self.end_token is not None:
+            text = text.replace(self.end_token, "")
+        return text
+
+
+class BatchTextTransformer(nn.Module):
+    def __init__(self, tokens: List[str], blank_token: str = "<blank>", pad_token: str = None,
+                 unknown_token: str = None, start_token: str = None, end_token: str = None,
+                 sentencepiece_model: Optional[str] = None, custom_tokenizer_function=None):
+        super().__init__()
+        if sentencepiece_model is not None or custom_tokenizer_function is not None:
+            raise NotImplementedError("tokenisers (text encoding for training) are outside the forward hot path")
+        self.vocab = Vocabulary(tokens, blank_token, pad_token, unknown_token, start_token, end_token)
+
+    @property
+    def num_tokens(self) -> int:
+        return len(self.vocab.itos)
+
+    def _finish(self, row) -> str:
+        out = "".join(self.vocab.itos[int(i)] for i in row)
+        out = out.replace("▁", " ")   # sentencepiece word boundary
+        out = out.replace("|", " ")   # huggingface word boundary
+        return self.vocab.remove_special_tokens(out)
+
+    def decode_collapsed(self, collapsed: Tensor, counts: Tensor) -> List[str]:
+        """Detokenise the output of ``thunder_b200::ctc_greedy`` (repeats already collapsed on the GPU):
+        ONE device-to-host copy, then the reference's string rules."""
+        col = collapsed.cpu().numpy()
+        cnt = counts.cpu().numpy()
+        return [self._finish(col[b, : cnt[b]]) for b in range(col.shape[0])]
+
+    def decode_prediction(self, predictions: Tensor, remove_repeated: bool = True) -> List[str]:
+        """Reference-compatible entry point on argmax ids ``[batch, time]`` (transform.py:93-122)."""
+        ids = predictions.detach().cpu().numpy()
+        out = []
+        for row in ids:
+            if remove_repeated and row.size:
+                keep = np.ones(row.shape[0], bool)
+                keep[1:] = row[1:] != row[:-1]
+                row = row[keep]
+            out.append(self._finish(row))
+        return out
