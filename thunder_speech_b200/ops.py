@@ -17,6 +17,28 @@ from . import _lib
 
 NS = "thunder_b200"
 
+#: when set to a list, every kernel-launching op appends (kernel name, meta dict, start event, end event);
+#: used by bench.py's per-kernel roofline pass (CUDA events on the launching stream).
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name: str, **meta):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.meta, self.e0, e1))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -140,9 +162,10 @@ def dw_conv(x: Tensor, T_in: int, weight: Tensor, stride: int, dilation: int, pa
     K = weight.shape[1]
     T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
     out = torch.empty((B, C, row_pitch(max(T_out, 1))), device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().ts_dw_conv(_ptr(x), B, C, T_in, pitch, _ptr(weight), K, stride, dilation, padding,
-                                     _ptr(lens) if lens is not None else None, _ptr(out), out.shape[2], _stream()),
-               "ts_dw_conv")
+    with _timed("dw_conv", bytes=2 * B * C * (T_in + T_out), flops=2 * B * C * T_out * K, K=K, C=C, T=T_out):
+        _lib.check(_lib.lib().ts_dw_conv(_ptr(x), B, C, T_in, pitch, _ptr(weight), K, stride, dilation, padding,
+                                         _ptr(lens) if lens is not None else None, _ptr(out), out.shape[2],
+                                         _stream()), "ts_dw_conv")
     return out
 
 
@@ -175,9 +198,12 @@ def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], 
     def P(t):
         return _ptr(t) if t is not None else None
 
-    _lib.check(_lib.lib().ts_pw_gemm(_ptr(w0), _ptr(x0), cin0, p0, P(w1), P(x1), cin1, p1, B, Cout, T, P(shift),
-                                     P(lens), _ptr(out), dt, pitch, int(relu), P(pool), P(se_scale), P(y1),
-                                     y1.shape[2] if y1 is not None else 0, _stream()), "ts_pw_gemm")
+    kin = cin0 + cin1
+    nbytes = 2 * B * T * kin + 2 * Cout * kin + (4 if out_f32 else 2) * B * T * Cout + (2 * B * T * Cout if y1 is not None else 0)
+    with _timed("pw_gemm", bytes=nbytes, flops=2 * B * T * kin * Cout, K=kin, C=Cout, T=T):
+        _lib.check(_lib.lib().ts_pw_gemm(_ptr(w0), _ptr(x0), cin0, p0, P(w1), P(x1), cin1, p1, B, Cout, T, P(shift),
+                                         P(lens), _ptr(out), dt, pitch, int(relu), P(pool), P(se_scale), P(y1),
+                                         y1.shape[2] if y1 is not None else 0, _stream()), "ts_pw_gemm")
     return out
 
 

@@ -1,0 +1,126 @@
+"""Model builders for the benchmark / smoke configurations and the bench workload object.
+
+``build_model(name)`` assembles the reference architectures named in BASELINE.json from this package's module
+shells with random-init weights from ``synth`` (no checkpoints offline):
+
+    quartznet5x5   QuartznetEncoder(repeat_blocks=1), 64 mel, V=29      (config 1)
+    quartznet15x5  QuartznetEncoder(repeat_blocks=3), 64 mel, V=29      (config 3)
+    citrinet1024   CitrinetEncoder(NeMo citrinet_1024 body), 80 mel, V=1025 (config 4)
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import _lib, ops, synth
+from .blocks import conv1d_decoder
+from .citrinet.blocks import CitrinetEncoder
+from .module import CTCModule
+from .quartznet.blocks import QuartznetEncoder
+from .quartznet.transform import FilterbankFeatures
+from .text_processing import BatchTextTransformer
+
+
+def _load(module, state: Dict[str, np.ndarray]):
+    module.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
+    return module
+
+
+def build_model(name: str, device, seed: int = 0) -> CTCModule:
+    if name in ("quartznet5x5", "quartznet15x5"):
+        rep = 1 if name == "quartznet5x5" else 3
+        enc = _load(QuartznetEncoder(repeat_blocks=rep),
+                    synth.encoder_state(synth.quartznet_block_list(repeat_blocks=rep), seed=seed))
+        dec = conv1d_decoder(1024, 29)
+        dec.load_state_dict({k: torch.from_numpy(v) for k, v in synth.decoder_state(1024, 29, seed + 1).items()})
+        fb = FilterbankFeatures(nfilt=64)
+        tt = BatchTextTransformer(synth.quartznet_vocab())
+    elif name == "citrinet1024":
+        c = synth.CITRINET_1024
+        enc = _load(CitrinetEncoder(c["filters"], c["kernel_sizes"], c["strides"], feat_in=80),
+                    synth.encoder_state(synth.citrinet_block_list(c["filters"], c["kernel_sizes"], c["strides"], 80),
+                                        seed=seed, se=True))
+        dec = conv1d_decoder(640, 1025)
+        dec.load_state_dict({k: torch.from_numpy(v) for k, v in synth.decoder_state(640, 1025, seed + 1).items()})
+        fb = FilterbankFeatures(nfilt=80)
+        tt = BatchTextTransformer(synth.citrinet_vocab(1024))
+    else:
+        raise ValueError(name)
+    return CTCModule(enc, dec, fb, tt).eval().to(device)
+
+
+class ModelWorkload:
+    """bench.py workload: ``predict()`` of a full model on a per-GPU batch of synthetic audio."""
+
+    NBUF = 2
+    dtype = "bf16"
+
+    def __init__(self, name, B, N, nfilt, dev, rank):
+        self.name, self.B, self.N, self.dev = name, B, N, dev
+        self.model = build_model(name, dev)
+        host = torch.from_numpy(synth.audio(B, N, 1234 + rank, "noise"))
+        self.host_audio = host.pin_memory()
+        self.audio = [(self.host_audio.to(dev) * (1.0 + 0.01 * i)).contiguous() for i in range(self.NBUF)]
+        self.stage = torch.empty((B, N), dtype=torch.float32, device=dev)
+        self.h2d_bytes = B * N * 4
+        ids, col, cnt = self.model.predict_ids_graphed(self.audio[0])
+        torch.cuda.synchronize()
+        self.T_out = col.shape[1]
+        self.d2h_bytes = col.numel() * 8 + cnt.numel() * 4
+        self.l2_note = (f"audio batch {B * N * 4 / 1e6:.0f} MB and every activation tensor exceed the 126 MB L2; "
+                        f"inputs rotate over {self.NBUF} buffers")
+        self._graph = self.model._graphs[(B, N)]
+
+    def graph_launches(self) -> int:
+        return self._graph.kernels_per_replay * self._graph.replays
+
+    def step_device(self, i):
+        return self.model.predict_ids_graphed(self.audio[i % self.NBUF])
+
+    def step_host(self, i):
+        """The user call: host audio in, transcriptions out."""
+        self.stage.copy_(self.host_audio, non_blocking=True)
+        return self.model.predict_graphed(self.stage)
+
+    def roofline(self, steps):
+        """Eager pass with CUDA events around every kernel launch; reports the kernel class with the largest
+        share of the step against its own roofline (HBM for depthwise, tensor for the GEMMs)."""
+        ops.PROFILE = []
+        n = max(2, min(steps, 3))
+        try:
+            for i in range(n):
+                self.model.predict_ids(self.audio[i % self.NBUF])
+            torch.cuda.synchronize()
+            recs = ops.PROFILE
+        finally:
+            ops.PROFILE = None
+        agg = {}
+        for name, meta, e0, e1 in recs:
+            a = agg.setdefault(name, dict(ms=0.0, bytes=0, flops=0, calls=0))
+            a["ms"] += e0.elapsed_time(e1)
+            a["bytes"] += meta["bytes"]
+            a["flops"] += meta["flops"]
+            a["calls"] += 1
+        total_ms = sum(a["ms"] for a in agg.values())
+        shares = {k: {"ms_per_step": a["ms"] / n, "share": a["ms"] / total_ms, "launches_per_step": a["calls"] // n,
+                      "GBps": a["bytes"] / (a["ms"] * 1e-3) / 1e9, "TFLOPs": a["flops"] / (a["ms"] * 1e-3) / 1e12}
+                  for k, a in agg.items()}
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        a = agg[top]
+        if top == "pw_gemm":
+            out = {"kernel": "pw_gemm_kernel", "bound": "tensor", "achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12,
+                   "unit": "TFLOP/s", "algorithmic_flops_per_step": a["flops"] // n}
+        else:
+            out = {"kernel": "dw_fast_kernel", "bound": "hbm", "achieved": a["bytes"] / (a["ms"] * 1e-3) / 1e9,
+                   "unit": "GB/s", "algorithmic_bytes_per_step": a["bytes"] // n}
+        out["avg_kernel_ms"] = a["ms"] / a["calls"]
+        out["launches_per_step"] = a["calls"] // n
+        out["traffic"] = None
+        out["per_kernel"] = shares
+        return out
+
+
+def make_bench_workload(name, B, N, nfilt, dev, rank):
+    return ModelWorkload(name, B, N, nfilt, dev, rank)
