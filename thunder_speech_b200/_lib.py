@@ -29,6 +29,7 @@ SIGNATURES = {
     "ts_last_error": (c_char_p, []),
     "ts_launch_count": (c_int64, []),
     "ts_row_pitch": (c_int, [c_int]),
+    "ts_set_option": (c_int, [c_char_p, c_int]),
     "ts_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ts_feature_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
@@ -84,3 +85,7 @@ def launch_count() -> int:
 
 def row_pitch(T: int) -> int:
     return int(lib().ts_row_pitch(int(T)))
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().ts_set_option(name.encode(), int(value)), "ts_set_option")

@@ -2,6 +2,7 @@
 #include "ts_common.cuh"
 
 #include <atomic>
+#include <string.h>
 
 namespace ts {
 
@@ -16,9 +17,21 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_dw_mma{1};
+int option_dw_mma() { return g_opt_dw_mma.load(std::memory_order_relaxed); }
+
 }  // namespace ts
 
 extern "C" const char* ts_version(void) { return "thunder_b200 0.1 (sm_100a)"; }
 extern "C" const char* ts_last_error(void) { return ts::g_err; }
 extern "C" int64_t ts_launch_count(void) { return ts::g_launches.load(std::memory_order_relaxed); }
 extern "C" int ts_row_pitch(int T) { return T <= 0 ? 0 : ts::round_up(T, ts::kRowPitchAlign); }
+
+extern "C" int ts_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "dw_mma") == 0) {
+    ts::g_opt_dw_mma.store(value);
+    return TS_OK;
+  }
+  ts::set_error("ts_set_option: unknown option '%s'", name ? name : "(null)");
+  return TS_ERR_INVALID;
+}

@@ -177,6 +177,10 @@ int launch_fast(const __nv_bfloat16* x, int B, int C, int T_in, int pitch_in, co
 }  // namespace dw
 }  // namespace ts
 
+namespace ts {
+int launch_dw_mma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
+                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
+}
 using namespace ts;
 
 #define TS_DW_CASE(KK, SS, DD)                                                                            \
@@ -197,6 +201,11 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
+  // stride-1 / dilation-1 / odd-K "same" convolutions: Toeplitz MMA on the tensor cores (dwmma.cu)
+  if (S == 1 && D == 1 && option_dw_mma()) {
+    const int rc = launch_dw_mma(xb, B, C, T_in, pitch_in, w, K, P, len_in, yb, pitch_out, st);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   // QuartzNet (quartznet/blocks.py:341-410)
   TS_DW_CASE(33, 2, 1) TS_DW_CASE(33, 1, 1) TS_DW_CASE(39, 1, 1) TS_DW_CASE(51, 1, 1) TS_DW_CASE(63, 1, 1)
   TS_DW_CASE(75, 1, 1) TS_DW_CASE(87, 1, 2)
