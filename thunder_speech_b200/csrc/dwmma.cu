@@ -101,10 +101,10 @@ dw_mma_kernel(const Params p) {
       }
       *reinterpret_cast<uint4*>(sB + q * BQ + col * 1024 + r * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    // rows 128..130 of every A stage are only ever read as halo garbage rows; zero them once so no NaN bit
-    // patterns can reach the accumulator rows we do store (they never do, rows are independent) -- hygiene only
-    for (int ci = tid; ci < NSTAGE * 8 * 3; ci += THREADS) {
-      const int s = ci / 24, col = (ci / 3) & 7, r = MROWS + ci % 3;
+    // stage rows beyond the stacked utterances only feed accumulator rows that are never stored; zero them once
+    const int r0 = p.NB * p.R, nz = AROWS - r0;  // rows the loaders never touch
+    for (int ci = tid; ci < NSTAGE * 8 * nz; ci += THREADS) {
+      const int s = ci / (8 * nz), col = (ci / nz) & 7, r = r0 + ci % nz;
       *reinterpret_cast<uint4*>(sA + s * A_STAGE + col * COLB + r * 16) = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
@@ -131,28 +131,32 @@ dw_mma_kernel(const Params p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===== loaders: 128 threads, 130 rows x 8 chunks per tile =====
+    // ===== loaders: 128 threads; thread geometry (row-in-utterance m, chunk column) is loop invariant =====
     const __nv_bfloat16* xc = p.x + (size_t)c * p.pitch;
     const size_t bstride = (size_t)p.C * p.pitch;
+    const int rchunks = p.R * 8;  // 16-byte chunks per stacked utterance
     for (int n = 0; n < ntiles; ++n) {
       const int s = n % NSTAGE;
       ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1);
       const int b0 = (tile0 + n) * p.NB;
       const uint32_t dst0 = ptx::smem_u32(sA + s * A_STAGE);
-      for (int ci = tid; ci < (MROWS + 2) * 8; ci += NLOAD) {
-        const int row = ci >> 3, col = ci & 7;
-        const int bl = row / p.R, m = row - bl * p.R;
-        const int b = b0 + bl;
+      for (int ch = tid; ch < rchunks; ch += NLOAD) {
+        const int m = ch >> 3, col = ch & 7;
         const int t = 64 * (m - 1) + 8 * col;
-        int nbytes = 0;
-        const __nv_bfloat16* src = p.x;
-        if (bl < p.NB && b < p.B && t >= 0) {
-          int lin = p.T;
-          if (p.lens) lin = min(lin, max(p.lens[b], 0));
-          nbytes = min(max((lin - t) * 2, 0), 16);
-          if (nbytes > 0) src = xc + b * bstride + t;
+        const uint32_t dst = dst0 + col * COLB + m * 16;
+        const __nv_bfloat16* src = xc + (size_t)b0 * bstride + t;
+#pragma unroll 3
+        for (int bl = 0; bl < p.NB; ++bl) {
+          const int b = b0 + bl;
+          int nbytes = 0;
+          if (b < p.B && t >= 0) {
+            int lin = p.T;
+            if (p.lens) lin = min(lin, max(__ldg(p.lens + b), 0));
+            nbytes = min(max((lin - t) * 2, 0), 16);
+          }
+          cp_async_16_zfill(dst + bl * p.R * 16, nbytes > 0 ? (const void*)(src + bl * bstride) : (const void*)p.x,
+                            nbytes);
         }
-        cp_async_16_zfill(dst0 + col * COLB + row * 16, src, nbytes);
       }
       cp_async_commit();
       if (n > 0) {  // publish the previous tile once its copies have landed
@@ -200,37 +204,50 @@ dw_mma_kernel(const Params p) {
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
     const int bl = row / p.R, i = row - bl * p.R;
+    const int t = 64 * i;
+    const bool row_ok = bl < p.NB && i < p.W;
     for (int n = 0; n < ntiles; ++n) {
       const int a = n % ACC_STAGES;
+      const int b = (tile0 + n) * p.NB + bl;
+      int lout = p.T;  // fetched before the wait so its latency hides behind the MMA
+      if (row_ok && b < p.B && p.lens) lout = min(lout, max(__ldg(p.lens + b), 0));
       ptx::mbar_wait(&acc_full[a], (n / ACC_STAGES) & 1);
       ptx::tc_fence_after();
-      uint32_t v0[32], v1[32];
+      uint32_t v[64];
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * L);
-      ptx::tmem_ld_32x32(taddr, v0);
-      ptx::tmem_ld_32x32(taddr + 32, v1);
+      ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[a]);  // accumulator stage can be overwritten
-      const int b = (tile0 + n) * p.NB + bl;
-      if (bl < p.NB && b < p.B && i < p.W) {
-        int lout = p.T;
-        if (p.lens) lout = min(lout, max(p.lens[b], 0));
-        const int t = 64 * i;
+      if (row_ok && b < p.B) {
         uint4* o = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.C + c) * p.pitch + t);
+        if (t + 64 <= lout) {  // interior window: no masking
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint32_t pk[4];
+          for (int g = 0; g < 8; ++g) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int e = g * 8 + 2 * h;
-            float lo = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]);
-            float hi = __uint_as_float(e + 1 < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]);
-            if (t + e >= lout) lo = 0.f;
-            if (t + e + 1 >= lout) hi = 0.f;
-            __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
-            pk[h] = *reinterpret_cast<uint32_t*>(&pr);
+            for (int h = 0; h < 4; ++h) {
+              __nv_bfloat162 pr = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * h]),
+                                                        __uint_as_float(v[g * 8 + 2 * h + 1]));
+              pk[h] = *reinterpret_cast<uint32_t*>(&pr);
+            }
+            o[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          o[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {  // window crossing (or beyond) the utterance end: frames >= lout are stored as zero
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int e = g * 8 + 2 * h;
+              const float lo = (t + e < lout) ? __uint_as_float(v[e]) : 0.f;
+              const float hi = (t + e + 1 < lout) ? __uint_as_float(v[e + 1]) : 0.f;
+              __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
+              pk[h] = *reinterpret_cast<uint32_t*>(&pr);
+            }
+            o[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
       }
       __syncwarp();
@@ -259,11 +276,24 @@ int launch_dw_mma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
   if (p.R > dwt::MROWS) return TS_ERR_UNSUPPORTED;  // rows longer than 8064 frames: SIMT path
   p.NB = dwt::MROWS / p.R;
   p.tiles_per_chan = ceil_div(B, p.NB);
-  // aim at >= 2 CTAs per SM worth of blocks while keeping the Toeplitz build amortised over several tiles
-  int groups = ceil_div(148 * 2 * 2, C);
-  groups = max(1, min(groups, p.tiles_per_chan));
-  p.tiles_per_cta = ceil_div(p.tiles_per_chan, groups);
-  groups = ceil_div(p.tiles_per_chan, p.tiles_per_cta);
+  // CTAs = C x groups; pick tiles-per-CTA for wave efficiency (2 CTAs/SM x 148 SMs per wave) while amortising the
+  // per-CTA Toeplitz build (about one tile's worth of work) over several tiles
+  {
+    double best = -1.0;
+    int best_tpc = p.tiles_per_chan;
+    for (int tpc = 1; tpc <= p.tiles_per_chan; ++tpc) {
+      const int g = ceil_div(p.tiles_per_chan, tpc);
+      const double waves = (double)C * g / 296.0;
+      const double eff = waves / (double)((long long)(waves + 0.999999)) * (double)p.tiles_per_chan / (double)(g * tpc) *
+                         (double)tpc / (double)(tpc + 1);
+      if (eff > best + 1e-9) {
+        best = eff;
+        best_tpc = tpc;
+      }
+    }
+    p.tiles_per_cta = best_tpc;
+  }
+  const int groups = ceil_div(p.tiles_per_chan, p.tiles_per_cta);
   static bool attr_set = false;
   if (!attr_set) {
     TS_CUDA(cudaFuncSetAttribute(dwt::dw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwt::SMEM_BYTES));
