@@ -1,0 +1,227 @@
+"""CPU tests of everything that runs on the host: C-ABI library load + exported symbols, module shells and
+their state_dict contract, BatchNorm folding, mel/window tables, greedy-decode string rules, length formulas,
+batch sharding over gloo (world_size 2).  No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as R
+from thunder_speech_b200 import _lib, synth
+from thunder_speech_b200.blocks import conv1d_decoder, conv_out_length, get_same_padding, lengths_to_mask
+from thunder_speech_b200.citrinet.blocks import CitrinetBlock, CitrinetEncoder
+from thunder_speech_b200.fused import build_block_plan
+from thunder_speech_b200.parallel import shard_bounds
+from thunder_speech_b200.quartznet.blocks import QuartznetBlock, QuartznetEncoder
+from thunder_speech_b200.quartznet.transform import FilterbankFeatures, mel_filterbank
+from thunder_speech_b200.text_processing import BatchTextTransformer, Vocabulary
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "thunder_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.lib()                       # raises loudly if the .so is missing
+    declared = header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/thunder_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert sorted(_lib.SIGNATURES) == declared
+    assert b"sm_100a" in lib.ts_version()
+    assert _lib.row_pitch(751) == 768 and _lib.row_pitch(64) == 64 and _lib.row_pitch(1) == 64
+    assert _lib.launch_count() >= 0
+    # argument errors are reported without touching a GPU
+    rc = lib.ts_set_option(b"no_such_option", 1)
+    assert rc == _lib.TS_ERR_INVALID and b"unknown option" in lib.ts_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib.ts_dw_conv(1, 1, 4, 50, 64, 1, 3, 2, 2, 1, None, 1, 64, None), "ts_dw_conv")  # stride & dilation > 1
+
+
+def test_library_has_no_libcuda_link_dependency():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out          # driver entry points are resolved at run time
+
+
+def test_ops_refuse_cpu_tensors():
+    from thunder_speech_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pack_rows(torch.zeros(1, 2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FilterbankFeatures().eval()(torch.zeros(1, 2000), torch.tensor([2000]))
+
+
+def test_filterbank_tables_and_state_dict_contract(golden_features):
+    fb = FilterbankFeatures(nfilt=64)
+    assert list(fb.state_dict().keys()) == ["1.window", "2.layer.0.fb"]
+    assert fb[2].layer[0].fb.shape == (1, 64, 257)
+    assert np.abs(fb[2].layer[0].fb[0].numpy() - golden_features["fb64"]).max() < 5e-6 * golden_features["fb64"].max()
+    assert np.abs(mel_filterbank(257, 80, 16000, 0.0, 8000.0).numpy() - golden_features["fb80"]).max() < 2e-7
+    assert np.abs(fb[1].window.numpy() - golden_features["window320"]).max() < 1e-7
+    t = fb._device_tables(torch.device("cpu"))
+    assert (t["win_lo"], t["win_hi"]) == (97, 415)                            # hann endpoints are exactly zero
+    # sparse bank reproduces the dense one
+    dense = np.zeros((64, 257), np.float32)
+    for m in range(64):
+        s, c, o = int(t["mel_start"][m]), int(t["mel_count"][m]), int(t["mel_off"][m])
+        dense[m, s:s + c] = t["mel_w"][o:o + c].numpy()
+    assert np.array_equal(dense, fb[2].layer[0].fb[0].numpy())
+    assert torch.equal(fb[1].get_sequence_length(torch.tensor([0, 159, 160, 320000])), torch.tensor([1, 1, 2, 2001]))
+    with pytest.raises(ValueError):
+        FilterbankFeatures(n_window_stride=0)
+    with pytest.raises(ValueError):
+        FilterbankFeatures(num_cutout_masks=2, num_freq_masks=1)
+
+
+def test_length_helpers_match_reference(golden_helpers):
+    g = golden_helpers
+    assert np.array_equal(lengths_to_mask(torch.from_numpy(g["mask_lengths"]), 6).numpy(), g["mask"])
+    for row, (k, s, d, p) in zip(g["seq_len_out"], g["same_padding"]):
+        assert get_same_padding(int(k), int(s), int(d)) == int(p)
+        got = conv_out_length(torch.from_numpy(g["seq_len_in"]), int(k), int(s), int(p), int(d))
+        assert np.array_equal(got.numpy(), row)
+        assert [conv_out_length(int(v), int(k), int(s), int(p), int(d)) for v in g["seq_len_in"]] == list(row)
+    with pytest.raises(ValueError):
+        get_same_padding(3, 2, 2)
+
+
+def test_encoders_load_reference_state_dicts_strictly():
+    enc = QuartznetEncoder(repeat_blocks=1)
+    st = synth.encoder_state(synth.quartznet_block_list(repeat_blocks=1), seed=5)
+    enc.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    assert sum(p.numel() for p in enc.parameters()) == 6683456                 # SURVEY.md 8 a10 [probe]
+    assert sum(p.numel() for p in QuartznetEncoder(repeat_blocks=3).parameters()) == 18894656
+    keys = list(enc.state_dict().keys())
+    assert "0.mconv.0.conv.weight" in keys and "0.mconv.1.conv.weight" in keys
+    assert "0.mconv.2.layer.0.running_var" in keys and "1.res.0.conv.weight" in keys and "1.res.1.layer.0.bias" in keys
+    c = synth.CITRINET_1024
+    cn = CitrinetEncoder(c["filters"], c["kernel_sizes"], c["strides"])
+    assert sum(p.numel() for p in cn.parameters()) == 139624336               # 139.6 M, SURVEY.md 8 a12
+    assert "1.mconv.23.layer.0.fc.0.weight" in cn.state_dict() and "1.mconv.23.layer.0.fc.2.weight" in cn.state_dict()
+    d = conv1d_decoder(1024, 29)
+    assert list(d.state_dict().keys()) == ["weight", "bias"] and d.weight.shape == (29, 1024, 1)
+
+
+def test_block_plan_folds_batchnorm_exactly():
+    rng = np.random.Generator(np.random.PCG64(42))
+    st = synth.block_state(rng, "", 16, 24, 3, 5, True, True, se=True)
+    blk = CitrinetBlock(16, 24, repeat=3, kernel_size=(5,), stride=(2,), residual=True, separable=True).eval()
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    plan = build_block_plan(blk)
+    assert [(s.K, s.S, s.D, s.P) for s in plan.subs] == [(5, 1, 1, 2), (5, 1, 1, 2), (5, 2, 1, 2)]   # stride on the last only
+    assert plan.res_stride == 2 and plan.se_w1.shape == (3, 24) and plan.se_w2.shape == (24, 3)
+    # folded pointwise == BN(conv1x1(x)) on a random vector (fp32 reference of the folding algebra)
+    x = torch.randn(2, 24, 7)
+    pw, bn = blk.mconv[6], blk.mconv[7].layer[0]
+    ref = bn(pw.conv(x))
+    sub = plan.subs[1]
+    got = torch.einsum("oc,bct->bot", sub.pw_w.float(), x) + sub.shift[None, :, None]
+    assert (got - ref).abs().max() < 2e-2 * ref.abs().max()                 # bf16 weights
+    scale = bn.weight / torch.sqrt(bn.running_var + 1e-3)
+    assert torch.allclose(sub.shift, bn.bias - bn.running_mean * scale, atol=1e-6)
+    qb = QuartznetBlock(8, 8, repeat=2, kernel_size=(3,), stride=(2,), residual=True, separable=True).eval()
+    assert build_block_plan(qb).res_stride == 4                               # stride ** repeat (quartznet/blocks.py:301)
+    with pytest.raises(NotImplementedError):
+        build_block_plan(QuartznetBlock(8, 8, repeat=1, kernel_size=(11,), separable=False).eval())
+
+
+def test_greedy_decode_string_rules(golden_decode):
+    tt = BatchTextTransformer(synth.quartznet_vocab())
+    assert tt.vocab.blank_idx == 28 and tt.num_tokens == 29
+    assert tt.decode_prediction(torch.from_numpy(golden_decode["ids"])) == list(golden_decode["text"])
+    tb = BatchTextTransformer(synth.citrinet_vocab(64))
+    assert tb.decode_prediction(torch.from_numpy(golden_decode["ids_bpe"])) == list(golden_decode["text_bpe"])
+    # reference known answers (tests/text/test_transforms.py:59-91)
+    v = BatchTextTransformer([" "] + [chr(c) for c in range(97, 123)], "<blank>", "<blank>", "<unk>", "<bos>", "<eos>")
+    blank = torch.full((1, 100), v.vocab.blank_idx)
+    assert v.decode_prediction(blank) == [""]
+    x = blank.clone(); x[:, :10] = v.vocab.stoi["a"]; x[:, 15:20] = v.vocab.stoi["b"]
+    assert v.decode_prediction(x) == ["ab"]
+    x = blank.clone(); x[:, :10] = v.vocab.stoi["a"]; x[:, 15:20] = v.vocab.stoi["a"]
+    assert v.decode_prediction(x) == ["aa"]
+    assert Vocabulary(["a", "b", "c"]).blank_idx == 3                         # tests/text/test_vocab.py:108-112
+    # collapsed-ids entry point used by predict(): same strings
+    ids = golden_decode["ids"]
+    rows = R.ctc_collapse(ids)
+    col = np.full(ids.shape, -1, np.int64)
+    for b, r in enumerate(rows):
+        col[b, :len(r)] = r
+    cnt = np.array([len(r) for r in rows], np.int32)
+    assert tt.decode_collapsed(torch.from_numpy(col), torch.from_numpy(cnt)) == list(golden_decode["text"])
+
+
+def test_torch_port_matches_reference_golden(golden_features, golden_e2e):
+    """oracle/ref_torch.py (the cpu_baseline / --impl reference port) is pinned to the same golden vectors."""
+    from oracle import ref_torch as RT
+
+    x = synth.audio(3, 4800, 11, "noise")
+    lens = synth.ragged_lengths(3, 4800, 111)
+    f, fl = RT.features(torch.from_numpy(x), torch.from_numpy(lens))
+    assert np.abs(f.numpy() - golden_features["qn_noise.features"]).max() < 1e-4
+    assert np.array_equal(fl.numpy(), golden_features["qn_noise.lengths"])
+    cfgs = R.quartznet_cfgs(repeat_blocks=1)
+    st = RT.to_torch(synth.encoder_state(synth.quartznet_block_list(repeat_blocks=1), seed=5))
+    dec = RT.to_torch(synth.decoder_state(1024, 29, seed=6))
+    ids, logits, el = RT.predict_ids(torch.from_numpy(synth.audio(2, 12000, 21, "tones")), cfgs, st, dec["weight"],
+                                     dec["bias"], 64)
+    ref = golden_e2e["qn5x5.full.logits"]
+    assert np.abs(logits.numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    assert np.array_equal(ids.numpy(), golden_e2e["qn5x5.full.ids"])
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for n in (0, 1, 7, 128, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from thunder_speech_b200.parallel import sharded_predict, shard_bounds
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+audio = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4)
+calls = []
+def fake_predict(x):                       # stands in for CTCModule.predict on this rank's shard
+    calls.append(x.shape[0])
+    return ["utt%d" % int(r[0].item() // 4) for r in x]
+out = sharded_predict(fake_predict, audio)
+assert out == ["utt%d" % i for i in range(7)], out
+lo, hi = shard_bounds(7, 2, dist.get_rank())
+assert calls == [hi - lo]
+dist.barrier(); dist.destroy_process_group()
+print("rank", sys.argv[3], "ok")
+"""
+
+
+def test_sharded_predict_world_size_2_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks shard a batch with no data-path collective and gather the transcripts."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = str(s.getsockname()[1]); s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o

@@ -1,0 +1,37 @@
+"""Batch sharding for multi-GPU inference: one process per GPU, every utterance is independent
+in eval mode (per-channel BatchNorm affine, per-utterance SqueezeExcite and feature normalisation), so the
+path shards with NO data-path collective.  The only exchange is gathering the transcripts (host strings) --
+``torch.distributed.all_gather_object`` over whatever backend the job runs (NCCL on the GPU box, gloo in the CPU
+tests)."""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``n`` utterances: the first ``n % world`` ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad world/rank {world}/{rank}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sharded_predict(predict: Callable[[torch.Tensor], List[str]], audio: torch.Tensor,
+                    group=None) -> List[str]:
+    """Every rank holds the same ``audio[B, N]`` (host or device); each runs ``predict`` on its contiguous slice
+    and all ranks return the full list of ``B`` transcripts in the original order."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return predict(audio)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(audio.shape[0], world, rank)
+    local = predict(audio[lo:hi]) if hi > lo else []
+    parts: List[Sequence[str]] = [None] * world  # type: ignore[list-item]
+    dist.all_gather_object(parts, list(local), group=group)
+    out: List[str] = []
+    for p in parts:
+        out.extend(p)
+    return out
