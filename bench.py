@@ -172,6 +172,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     desc, B, secs, nfilt = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+        desc += f" [per-GPU batch overridden to {B}]"
     N = secs * SAMPLE_RATE
     from thunder_speech_b200 import bench_workloads as BW
 
@@ -265,6 +268,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (experiments only)")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = default_workload()

@@ -41,7 +41,8 @@ const char* ts_version(void);
 const char* ts_last_error(void);
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 int64_t ts_launch_count(void);
-/* runtime switches for A/B measurements: "dw_mma" (default 1) = stride-1 depthwise convs on the tensor cores */
+/* runtime switches for A/B measurements: "dw_mma" (default 1) = stride-1 depthwise convs on the tensor cores,
+ * "pw_big" (default 1) = persistent 256x256-tile GEMM for bf16 outputs with Cout > 128 */
 int ts_set_option(const char* name, int value);
 /* pitch (in frames) of a padded activation row holding T frames */
 int ts_row_pitch(int T);

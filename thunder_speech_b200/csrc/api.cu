@@ -18,7 +18,9 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static std::atomic<int> g_opt_dw_mma{1};
+static std::atomic<int> g_opt_pw_big{1};
 int option_dw_mma() { return g_opt_dw_mma.load(std::memory_order_relaxed); }
+int option_pw_big() { return g_opt_pw_big.load(std::memory_order_relaxed); }
 
 }  // namespace ts
 
@@ -30,6 +32,10 @@ extern "C" int ts_row_pitch(int T) { return T <= 0 ? 0 : ts::round_up(T, ts::kRo
 extern "C" int ts_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "dw_mma") == 0) {
     ts::g_opt_dw_mma.store(value);
+    return TS_OK;
+  }
+  if (name != nullptr && strcmp(name, "pw_big") == 0) {
+    ts::g_opt_pw_big.store(value);
     return TS_OK;
   }
   ts::set_error("ts_set_option: unknown option '%s'", name ? name : "(null)");
