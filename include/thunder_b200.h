@@ -42,7 +42,8 @@ const char* ts_last_error(void);
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 int64_t ts_launch_count(void);
 /* runtime switches for A/B measurements: "dw_mma" (default 1) = stride-1 depthwise convs on the tensor cores,
- * "pw_big" (default 1) = persistent 256x256-tile GEMM for bf16 outputs with Cout > 128 */
+ * "pw_big" (default 1) = persistent 256x256-tile GEMM for bf16 outputs with Cout > 128,
+ * "dw_tma" (default 1) = TMA-fed Toeplitz kernel for pre-masked inputs, "dw_base_offset" (descriptor experiment) */
 int ts_set_option(const char* name, int value);
 /* pitch (in frames) of a padded activation row holding T frames */
 int ts_row_pitch(int T);
@@ -81,9 +82,12 @@ int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int
  * output frames t' >= get_seq_len(len_in[b]) (the mask the following pointwise MaskedConv1d applies).
  *   x  bf16 rows [B, C, pitch_in] holding T_in frames     w  [C, K] f32     len_in [B] i32 or NULL (= all valid)
  *   y  bf16 rows [B, C, pitch_out], T_out = floor((T_in + 2P - D(K-1) - 1)/S) + 1
- * TS_ERR_INVALID when both S > 1 and D > 1 (get_same_padding raises ValueError, src/thunder/blocks.py:192-193). */
+ * TS_ERR_INVALID when both S > 1 and D > 1 (get_same_padding raises ValueError, src/thunder/blocks.py:192-193).
+ *   flags: TS_DW_INPUT_PREMASKED = the caller guarantees x is already zero for t >= len_in[b] (true for rows
+ *          produced by ts_pack_rows / ts_pw_gemm / ts_feature_normalize with lengths): enables the TMA-fed kernel */
+#define TS_DW_INPUT_PREMASKED 1
 int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float* w, int K, int S, int D, int P,
-               const int32_t* len_in, void* y, int pitch_out, void* stream);
+               const int32_t* len_in, int flags, void* y, int pitch_out, void* stream);
 
 /* ---- (3) pointwise conv / residual / decoder GEMM (tcgen05 + TMEM + TMA) ------------------- */
 /* out[b, m, t] = epi( W0[m, :] . X0[b, :, t] + W1[m, :] . X1[b, :, t] + shift[m] )

@@ -45,7 +45,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     rc = lib.ts_set_option(b"no_such_option", 1)
     assert rc == _lib.TS_ERR_INVALID and b"unknown option" in lib.ts_last_error()
     with pytest.raises(ValueError):
-        _lib.check(lib.ts_dw_conv(1, 1, 4, 50, 64, 1, 3, 2, 2, 1, None, 1, 64, None), "ts_dw_conv")  # stride & dilation > 1
+        _lib.check(lib.ts_dw_conv(1, 1, 4, 50, 64, 1, 3, 2, 2, 1, None, 0, 1, 64, None), "ts_dw_conv")  # stride & dilation > 1
 
 
 def test_library_has_no_libcuda_link_dependency():

@@ -45,11 +45,11 @@ DW_FAST = [(33, 2, 1), (33, 1, 1), (39, 1, 1), (51, 1, 1), (63, 1, 1), (75, 1, 1
 DW_GENERIC = [(3, 1, 1, 1), (3, 2, 1, 1), (7, 1, 3, 9), (9, 1, 1, 0), (4, 1, 1, 2), (1, 1, 1, 0)]
 
 
-def run_dw(x, w, K, S, D, P, lens):
+def run_dw(x, w, K, S, D, P, lens, premasked=False):
     B, C, T = x.shape
-    xr = to_rows(x)
     l32 = None if lens is None else torch.from_numpy(lens.astype(np.int32)).cuda()
-    y = ops.dw_conv(xr, T, torch.from_numpy(w).cuda(), S, D, P, l32)
+    xr = ops.pack_rows(torch.from_numpy(x).cuda(), l32) if premasked else to_rows(x)
+    y = ops.dw_conv(xr, T, torch.from_numpy(w).cuda(), S, D, P, l32, premasked)
     T_out = (T + 2 * P - D * (K - 1) - 1) // S + 1
     torch.cuda.synchronize()
     return from_rows(y, T_out), y
@@ -68,7 +68,7 @@ def oracle_dw(x, w, K, S, D, P, lens):
 
 
 @pytest.mark.parametrize("K,S,D", DW_FAST)
-@pytest.mark.parametrize("T", [751, 300])
+@pytest.mark.parametrize("T", [751, 300, 2001])
 def test_dw_conv_fast_paths(K, S, D, T):
     rng = np.random.default_rng(K * 7 + S + D + T)
     B, C = 3, 5
@@ -76,12 +76,12 @@ def test_dw_conv_fast_paths(K, S, D, T):
     x = rng.standard_normal((B, C, T)).astype(np.float32)
     w = rng.uniform(-0.3, 0.3, (C, K)).astype(np.float32)
     lens = np.array([T, T * 2 // 3, 1], np.int64)
-    for ln in (None, lens):
-        got, rows = run_dw(x, w, K, S, D, P, ln)
+    for ln, pre in ((None, False), (lens, False), (lens, True)):   # unmasked / kernel-masked / caller-masked (TMA path)
+        got, rows = run_dw(x, w, K, S, D, P, ln, pre)
         ref = oracle_dw(x, w, K, S, D, P, ln)
         assert got.shape == ref.shape
         emax, _ = rel_err(got, ref)
-        assert emax < BF16_TOL, (K, S, D, T, emax)
+        assert emax < BF16_TOL, (K, S, D, T, pre, emax)
         assert (rows[:, :, ref.shape[-1]:].float() == 0).all()      # pad frames are zero
 
 

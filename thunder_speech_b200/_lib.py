@@ -19,6 +19,7 @@ TS_ERR_UNSUPPORTED = -2
 TS_ERR_NO_DEVICE = -3
 TS_F32 = 0
 TS_BF16 = 1
+TS_DW_INPUT_PREMASKED = 1
 
 _lib = None
 
@@ -35,7 +36,7 @@ SIGNATURES = {
     "ts_feature_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
                                      c_int, c_void_p, c_void_p]),
     "ts_dw_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                           c_void_p, c_int, c_void_p]),
+                           c_int, c_void_p, c_int, c_void_p]),
     "ts_pw_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p]),

@@ -180,6 +180,8 @@ int launch_fast(const __nv_bfloat16* x, int B, int C, int T_in, int pitch_in, co
 namespace ts {
 int launch_dw_mma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
+int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
+                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
 }
 using namespace ts;
 
@@ -188,7 +190,7 @@ using namespace ts;
     return dw::launch_fast<KK, SS, DD>(xb, B, C, T_in, pitch_in, w, len_in, yb, T_out, pitch_out, st);
 
 extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float* w, int K, int S, int D,
-                          int P, const int32_t* len_in, void* y, int pitch_out, void* stream) {
+                          int P, const int32_t* len_in, int flags, void* y, int pitch_out, void* stream) {
   TS_REQUIRE(x && w && y, TS_ERR_INVALID, "ts_dw_conv: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && T_in > 0 && K > 0 && S > 0 && D > 0 && P >= 0, TS_ERR_INVALID, "ts_dw_conv: bad sizes");
   TS_REQUIRE(!(S > 1 && D > 1), TS_ERR_INVALID, "Only stride OR dilation may be greater than 1");
@@ -202,6 +204,11 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
   // stride-1 / dilation-1 / odd-K "same" convolutions: Toeplitz MMA on the tensor cores (dwmma.cu)
+  // ... through TMA when the caller guarantees rows are already zero beyond len_in (or there are no lengths)
+  if (S == 1 && D == 1 && option_dw_mma() && option_dw_tma() && (len_in == nullptr || (flags & TS_DW_INPUT_PREMASKED))) {
+    const int rc = launch_dw_tma(xb, B, C, T_in, pitch_in, w, K, P, len_in, yb, pitch_out, st);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   if (S == 1 && D == 1 && option_dw_mma()) {
     const int rc = launch_dw_mma(xb, B, C, T_in, pitch_in, w, K, P, len_in, yb, pitch_out, st);
     if (rc != TS_ERR_UNSUPPORTED) return rc;

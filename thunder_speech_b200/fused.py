@@ -141,7 +141,7 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
     for r, sb in enumerate(plan.subs):
         last = r == n - 1
         if sb.dw_w is not None:
-            a = ops.dw_conv(cur, Tc, sb.dw_w, sb.S, sb.D, sb.P, lc)
+            a = ops.dw_conv(cur, Tc, sb.dw_w, sb.S, sb.D, sb.P, lc, True)  # rows are zero beyond lc
             Ta = conv_out_length(Tc, sb.K, sb.S, sb.P, sb.D)
             la = _next_lens(lc, sb.K, sb.S, sb.D, sb.P)
         else:
@@ -155,7 +155,7 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
         if plan.res_w is not None:
             xr = x_in
             if plan.res_stride > 1:  # 1x1 conv with stride: gather every stride-th (masked) input frame
-                xr = ops.dw_conv(x_in, T_in, plan.ones, plan.res_stride, 1, 0, lens_in)
+                xr = ops.dw_conv(x_in, T_in, plan.ones, plan.res_stride, 1, 0, lens_in, True)
         if plan.se_w1 is None:
             if xr is not None:
                 out = ops.pw_gemm(sb.pw_w, a, plan.res_w, xr, Ta, plan.total_shift, out_lens, False, True, None, None,

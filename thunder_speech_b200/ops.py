@@ -155,8 +155,9 @@ def lengths_i32(lengths: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------- depthwise
 @torch.library.custom_op(f"{NS}::dw_conv", mutates_args=())
 def dw_conv(x: Tensor, T_in: int, weight: Tensor, stride: int, dilation: int, padding: int,
-            lens: Optional[Tensor]) -> Tensor:
-    """Masked depthwise conv over bf16 rows.  ``weight`` is ``[C, K]`` f32; ``lens`` i32 ``[B]`` input lengths."""
+            lens: Optional[Tensor], premasked: bool = False) -> Tensor:
+    """Masked depthwise conv over bf16 rows.  ``weight`` is ``[C, K]`` f32; ``lens`` i32 ``[B]`` input lengths.
+    ``premasked``: the caller guarantees ``x`` is already zero beyond ``lens`` (enables the TMA-fed kernel)."""
     _need_cuda(x, weight)
     B, C, pitch = x.shape
     K = weight.shape[1]
@@ -164,13 +165,14 @@ def dw_conv(x: Tensor, T_in: int, weight: Tensor, stride: int, dilation: int, pa
     out = torch.empty((B, C, row_pitch(max(T_out, 1))), device=x.device, dtype=torch.bfloat16)
     with _timed("dw_conv", bytes=2 * B * C * (T_in + T_out), flops=2 * B * C * T_out * K, K=K, C=C, T=T_out):
         _lib.check(_lib.lib().ts_dw_conv(_ptr(x), B, C, T_in, pitch, _ptr(weight), K, stride, dilation, padding,
-                                         _ptr(lens) if lens is not None else None, _ptr(out), out.shape[2],
+                                         _ptr(lens) if lens is not None else None,
+                                         _lib.TS_DW_INPUT_PREMASKED if premasked else 0, _ptr(out), out.shape[2],
                                          _stream()), "ts_dw_conv")
     return out
 
 
 @dw_conv.register_fake
-def _(x, T_in, weight, stride, dilation, padding, lens):
+def _(x, T_in, weight, stride, dilation, padding, lens, premasked=False):
     K = weight.shape[1]
     T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
     return x.new_empty((x.shape[0], x.shape[1], row_pitch(max(T_out, 1))))
