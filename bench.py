@@ -205,14 +205,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------------------
-    for i in range(min(args.warmup, 3)):
-        wl.step_host(i)
+    wl.run_host(min(args.warmup, 3))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
-        wl.step_host(i)
+    wl.run_host(args.steps)
     e1.record()
     barrier()
     e2e_wall = time.perf_counter() - t0

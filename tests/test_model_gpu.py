@@ -141,3 +141,12 @@ def test_batch_independence():
     full, _ = m(x, lens)
     solo, _ = m(x[1:2].contiguous(), lens[1:2])
     assert torch.equal(full[1:2], solo)
+
+
+def test_predict_stream_matches_predict():
+    """The pipelined serving loop (H2D / compute / D2H overlapped) returns the same strings as predict()."""
+    m, _ = build_qn5x5()
+    xs = [torch.from_numpy(synth.audio(2, 9000, 40 + i, "tones")).pin_memory() for i in range(5)]
+    want = [m.predict(x.cuda()) for x in xs]
+    got = list(m.predict_stream(xs))
+    assert got == want

@@ -19,6 +19,10 @@ class _Base:
         """Kernel launches that happened inside CUDA-graph replays (not seen by ts_launch_count)."""
         return 0
 
+    def run_host(self, steps):
+        for i in range(steps):
+            self.step_host(i)
+
 
 class FeaturesWorkload(_Base):
     """BASELINE config 2: FilterbankFeatures only."""

@@ -11,7 +11,7 @@ class (module.py:102-189) is Lightning glue outside the forward hot path.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 
 import torch
 from torch import Tensor, nn
@@ -94,6 +94,60 @@ class CTCModule(nn.Module):
     def predict_graphed(self, x: Tensor) -> List[str]:
         _, col, cnt = self.predict_ids_graphed(x)
         return self.text_transform.decode_collapsed(col, cnt)
+
+    @torch.no_grad()
+    def predict_stream(self, batches: Iterable[Tensor]) -> Iterator[List[str]]:
+        """Serving loop over HOST batches ``[B, N]`` of one fixed shape (pinned memory for true overlap): the
+        host-to-device copy of batch i+1 runs on a copy stream while batch i computes (CUDA-graph replay), and the
+        detokenisation of batch i-1 runs on the CPU meanwhile.  Yields one ``List[str]`` per batch, in order."""
+        pipe = None
+        pending = []
+        for i, xb in enumerate(batches):
+            if pipe is None:
+                pipe = _StreamPipe(self, xb)
+            pending.append(pipe.submit(i, xb))
+            if len(pending) == 2:
+                yield pipe.collect(pending.pop(0))
+        while pending:
+            yield pipe.collect(pending.pop(0))
+
+
+class _StreamPipe:
+    """Double-buffered H2D / compute / D2H pipeline behind :meth:`CTCModule.predict_stream`."""
+
+    def __init__(self, module: CTCModule, example: Tensor):
+        self.m = module
+        dev = next(module.encoder.parameters()).device
+        B, N = example.shape
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty((B, N), device=dev, dtype=torch.float32) for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.stage_free = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(2)]
+        _, col, cnt = module.predict_ids_graphed(self.stage[0])   # builds / warms the graph for this shape
+        torch.cuda.synchronize(dev)
+        self.host_col = [torch.empty(col.shape, dtype=col.dtype).pin_memory() for _ in range(2)]
+        self.host_cnt = [torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory() for _ in range(2)]
+
+    def submit(self, i: int, xb: Tensor) -> int:
+        s = i % 2
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if i >= 2:
+                self.copy_stream.wait_event(self.stage_free[s])
+            self.stage[s].copy_(xb, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        cur.wait_event(self.h2d_done[s])
+        _, col, cnt = self.m.predict_ids_graphed(self.stage[s])
+        self.stage_free[s].record(cur)
+        self.host_col[s].copy_(col, non_blocking=True)
+        self.host_cnt[s].copy_(cnt, non_blocking=True)
+        self.d2h_done[s].record(cur)
+        return s
+
+    def collect(self, s: int) -> List[str]:
+        self.d2h_done[s].synchronize()
+        return self.m.text_transform.decode_collapsed(self.host_col[s], self.host_cnt[s])
 
 
 class _PredictGraph:

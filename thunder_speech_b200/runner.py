@@ -80,9 +80,18 @@ class ModelWorkload:
         return self.model.predict_ids_graphed(self.audio[i % self.NBUF])
 
     def step_host(self, i):
-        """The user call: host audio in, transcriptions out."""
+        """The single-shot user call: host audio in, transcriptions out (copy, compute, decode in sequence)."""
         self.stage.copy_(self.host_audio, non_blocking=True)
         return self.model.predict_graphed(self.stage)
+
+    def run_host(self, steps):
+        """The serving-loop user call: ``predict_stream`` over ``steps`` pinned host batches -- every step still
+        copies its own audio host->device and its token ids device->host inside the timed region; the copies
+        overlap the neighbouring steps' compute."""
+        n = 0
+        for texts in self.model.predict_stream(self.host_audio for _ in range(steps)):
+            n += len(texts)
+        return n
 
     def roofline(self, steps):
         """Eager pass with CUDA events around every kernel launch; reports the kernel class with the largest
