@@ -19,16 +19,24 @@
 namespace ts {
 namespace pw2 {
 
-constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int BM = 256, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 32 KB
-constexpr int B_BYTES = BK * BN * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int STG_BYTES = 32 * 128;           // one epilogue warp's staging tile: 32 rows x 64 bf16
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 + 1024;
 constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
+
+// BN = 256: one accumulator set (2 x 256 columns), 64 B/clk/SM of operand fill -- for tensor-bound (large K) GEMMs.
+// BN = 128: two accumulator sets, the epilogue of tile i overlaps the MMAs of tile i+1 -- for the HBM-bound
+//           small-K QuartzNet layers where the epilogue is as long as the main loop.
+template <int BN>
+struct Cfg {
+  static constexpr int ACC = TMEM_COLS / (2 * BN);
+  static constexpr int B_BYTES = BK * BN * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 + 1024;
+};
 
 struct Params {
   CUtensorMap a0, b0, a1, b1, out;
@@ -56,16 +64,20 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 pw_gemm_big_kernel(const __grid_constant__ Params p) {
+  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+  constexpr int ACC = Cfg<BN>::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_empty = tmem_full + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.kc0 + p.kc1;
@@ -84,8 +96,10 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full, 1);
-    ptx::mbar_init(tmem_empty, EPI_WARPS * 32);
+    for (int a = 0; a < ACC; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -125,7 +139,8 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 1);
     uint32_t cnt = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      ptx::mbar_wait(tmem_empty, (it & 1) ^ 1);   // epilogue has drained the previous tile's accumulators
+      const int a = it % ACC;
+      ptx::mbar_wait(&tmem_empty[a], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
       ptx::tc_fence_after();
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
         const int s = cnt % STAGES;
@@ -139,12 +154,12 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint64_t da = ptx::umma_desc(sa + h * (128 * BK * 2) + k * 32, 0, 1024);
-            ptx::mma_bf16_ss(tmem_base + h * BN, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            ptx::mma_bf16_ss(tmem_base + (a * 2 + h) * BN, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
           }
         }
         ptx::mma_commit(&empty_bar[s]);
       }
-      ptx::mma_commit(tmem_full);
+      ptx::mma_commit(&tmem_full[a]);
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
@@ -165,19 +180,20 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const float gate = (m_ok && p.se_scale) ? p.se_scale[(size_t)b * p.Cout + m] : 0.f;
       float pooled = 0.f;
-      ptx::mbar_wait(tmem_full, it & 1);
+      const int a = it % ACC;
+      ptx::mbar_wait(&tmem_full[a], (it / ACC) & 1);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < BN / 64; ++cc) {
         uint32_t v[64];
         __syncwarp();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + cc * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * 2 + h) * BN + cc * 64);
         ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         ptx::tmem_ld_wait();
         if (cc == BN / 64 - 1) {  // accumulators fully read: the MMA warp may start the next tile
           ptx::tc_fence_before();
-          ptx::mbar_arrive(tmem_empty);
+          ptx::mbar_arrive(&tmem_empty[a]);
         }
         const int tb = t0 + cc * 64;
         if (mrow0 < p.Cout && tb < p.out_pitch) {   // warp-uniform: something of this 32 x 64 block is stored
@@ -203,17 +219,22 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
           }
           if (lane == 0) bulk_wait_read0();   // previous TMA store has finished reading the staging tile
           __syncwarp();
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) r[j] = fmaxf(r[j], 0.f);
+          }
+          if (tb + 64 > len) {   // block crosses the utterance end (warp-uniform): zero the tail
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (tb + j >= len) r[j] = 0.f;
+          }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             uint32_t pk[4];
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
               const int j = g * 8 + 2 * hh;
-              float lo = r[j], hi = r[j + 1];
-              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-              if (tb + j >= len) lo = 0.f;
-              if (tb + j + 1 >= len) hi = 0.f;
-              __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
+              __nv_bfloat162 pr = __floats2bfloat162_rn(r[j], r[j + 1]);
               pk[hh] = *reinterpret_cast<uint32_t*>(&pr);
             }
             // SWIZZLE_128B: 16-byte chunk g of row `lane` lives at chunk (g ^ (row & 7))
@@ -252,6 +273,8 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
   pw2::Params p;
   memset(&p, 0, sizeof(p));
   int rc;
+  // tile width: 256 frames for tensor-bound (K >= 1024) GEMMs, 128 with double-buffered accumulators otherwise
+  const int BN = (cin0 + cin1 >= 1024) ? 256 : 128;
   if ((rc = tma::make_2d_bf16(&p.a0, w0, cin0, Cout, (uint64_t)cin0 * 2, pw2::BK, pw2::BM)) != TS_OK) return rc;
   if ((rc = tma::make_3d_bf16(&p.b0, x0, T, cin0, B, (uint64_t)x0_pitch * 2, (uint64_t)cin0 * x0_pitch * 2, 64, pw2::BK,
                               1)) != TS_OK)
@@ -270,7 +293,7 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
     return rc;
   p.Cout = Cout; p.T = T; p.B = B;
   p.m_tiles = ceil_div(Cout, pw2::BM);
-  p.n_tiles = ceil_div(out_pitch, pw2::BN);
+  p.n_tiles = ceil_div(out_pitch, BN);
   p.num_tiles = p.m_tiles * p.n_tiles * B;
   p.shift = shift; p.lens = lens; p.out_pitch = out_pitch; p.relu = relu;
   p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
@@ -280,10 +303,16 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
     int dev = 0;
     TS_CUDA(cudaGetDevice(&dev));
     TS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    TS_CUDA(cudaFuncSetAttribute(pw2::pw_gemm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pw2::SMEM_BYTES));
+    TS_CUDA(cudaFuncSetAttribute(pw2::pw_gemm_big_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 pw2::Cfg<128>::SMEM_BYTES));
+    TS_CUDA(cudaFuncSetAttribute(pw2::pw_gemm_big_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 pw2::Cfg<256>::SMEM_BYTES));
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  pw2::pw_gemm_big_kernel<<<grid, pw2::THREADS, pw2::SMEM_BYTES, st>>>(p);
+  if (BN == 256)
+    pw2::pw_gemm_big_kernel<256><<<grid, pw2::THREADS, pw2::Cfg<256>::SMEM_BYTES, st>>>(p);
+  else
+    pw2::pw_gemm_big_kernel<128><<<grid, pw2::THREADS, pw2::Cfg<128>::SMEM_BYTES, st>>>(p);
   TS_LAUNCH_CHECK("pw_gemm_big_kernel");
   return TS_OK;
 }
