@@ -119,10 +119,16 @@ int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, cons
 /* Greedy CTC: `pred.argmax(1)` (src/thunder/module.py:100; first maximal index, NaN maximal) followed by the
  * per-row torch.unique_consecutive of decode_prediction (src/thunder/text_processing/transform.py:107-110).
  *   logits [B, V, pitch] f32 or bf16 rows, T valid frames
- *   ids [B, T] i64 argmax (may be NULL); collapsed [B, T] i64 padded with -1; counts [B] i32
+ *   ids [B, T] i64 argmax; collapsed [B, T] i64 padded with -1; counts [B] i32
  *   drop_blank < 0 keeps blanks (the reference removes the blank token as a string, vocab.py:114-130) */
 int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch, int64_t* ids, int64_t* collapsed,
                   int32_t* counts, int drop_blank, void* stream);
+
+/* y[b, c, t'] = x[b, c, S t'] (zero for S t' >= min(T_in, len_in[b]) and in the pad): the input gather of a strided
+ * 1x1 residual conv, MaskedConv1d(kernel_size=1, stride=S) (citrinet/blocks.py:159-168, quartznet/blocks.py:301-311);
+ * its channel mixing then runs in ts_pw_gemm.  T_out = (T_in - 1) / S + 1 */
+int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_in, int S, const int32_t* len_in, void* y,
+                   int pitch_out, void* stream);
 
 /* ---- layout / length plumbing at module boundaries ------------------------------------------ */
 /* contiguous [B, C, T] (TS_F32 or TS_BF16) -> bf16 rows [B, C, pitch] (frames >= min(T, lens[b]) zero; lens may

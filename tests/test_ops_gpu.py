@@ -55,11 +55,13 @@ def run_dw(x, w, K, S, D, P, lens, premasked=False):
     return from_rows(y, T_out), y
 
 
-def oracle_dw(x, w, K, S, D, P, lens):
+def oracle_dw(x, w, K, S, D, P, lens, w_bf16=None):
     B, C, T = x.shape
     xb = bf16_round(x)
-    if S == 1 and D == 1 and K % 2 == 1 and P == K // 2:
-        w = bf16_round(w)   # the tensor-core (Toeplitz MMA) path holds the taps in bf16; the SIMT paths keep fp32
+    if w_bf16 is None:
+        w_bf16 = S == 1 and D == 1 and K % 2 == 1 and P == K // 2
+    if w_bf16:
+        w = bf16_round(w)   # the tensor-core (Toeplitz MMA) paths hold the taps in bf16; the SIMT paths keep fp32
     if lens is None:
         lens = np.full((B,), T)
     y, yl = R.masked_conv1d(xb, lens, w[:, None, :], S, P, D, groups=C)
@@ -78,7 +80,9 @@ def test_dw_conv_fast_paths(K, S, D, T):
     lens = np.array([T, T * 2 // 3, 1], np.int64)
     for ln, pre in ((None, False), (lens, False), (lens, True)):   # unmasked / kernel-masked / caller-masked (TMA path)
         got, rows = run_dw(x, w, K, S, D, P, ln, pre)
-        ref = oracle_dw(x, w, K, S, D, P, ln)
+        # dilated "same" convs run on the TMA Toeplitz kernel (bf16 taps) when the input is pre-masked / unmasked
+        tma = S == 1 and 2 * P == D * (K - 1) and (ln is None or pre)
+        ref = oracle_dw(x, w, K, S, D, P, ln, w_bf16=True if (tma and D > 1) else None)
         assert got.shape == ref.shape
         emax, _ = rel_err(got, ref)
         assert emax < BF16_TOL, (K, S, D, T, pre, emax)

@@ -180,7 +180,7 @@ int launch_fast(const __nv_bfloat16* x, int B, int C, int T_in, int pitch_in, co
 namespace ts {
 int launch_dw_mma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
-int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
+int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
 }
 using namespace ts;
@@ -205,8 +205,8 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   cudaStream_t st = (cudaStream_t)stream;
   // stride-1 / dilation-1 / odd-K "same" convolutions: Toeplitz MMA on the tensor cores (dwmma.cu)
   // ... through TMA when the caller guarantees rows are already zero beyond len_in (or there are no lengths)
-  if (S == 1 && D == 1 && option_dw_mma() && option_dw_tma() && (len_in == nullptr || (flags & TS_DW_INPUT_PREMASKED))) {
-    const int rc = launch_dw_tma(xb, B, C, T_in, pitch_in, w, K, P, len_in, yb, pitch_out, st);
+  if (S == 1 && option_dw_mma() && option_dw_tma() && (len_in == nullptr || (flags & TS_DW_INPUT_PREMASKED))) {
+    const int rc = launch_dw_tma(xb, B, C, T_in, pitch_in, w, K, D, P, len_in, yb, pitch_out, st);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
   }
   if (S == 1 && D == 1 && option_dw_mma()) {

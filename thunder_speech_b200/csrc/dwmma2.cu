@@ -20,19 +20,20 @@ constexpr int MROWS = 128;
 constexpr int A_STAGE = 17 * 1024;     // 130 rows x 128 B rounded up to a multiple of 1024
 constexpr int NSTAGE = 3;
 constexpr int BQ = 64 * 128;           // one Toeplitz block: 64 rows (r) x 64 k (j) bf16 = 8 KB
-constexpr int NQ = 3;
+constexpr int MAX_NQ = 5;              // Toeplitz blocks: left halo + centre + right halo windows (3 for K <= 129, dilation 1)
 constexpr int OUT_STAGE = MROWS * 128; // 16 KB
 constexpr int ACC_STAGES = 4;
 constexpr int TMEM_COLS = ACC_STAGES * L;  // 256
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = NSTAGE * A_STAGE + NQ * BQ + OUT_STAGE + 256 + 1024;
+__host__ __device__ constexpr int smem_bytes(int nq) { return NSTAGE * A_STAGE + nq * BQ + OUT_STAGE + 256 + 1024; }
 
 struct Params {
   CUtensorMap in, out;   // (64 frames, W windows, C, B), box (64, R, 1, NB)
   const float* w;
   const int32_t* lens;
-  int B, C, T, K, P;
+  int B, C, T, K, P, D;
   int W, R, NB;
+  int HL, NQ;            // left halo windows = ceil(P / 64); Toeplitz blocks = HL + 1 + (63 + P) / 64
   int tiles_per_chan, tiles_per_cta;
   int base_offset_mode;  // experiment switch, default 0: MEASURED on B200 -- a SW128 tile whose start is shifted by
                          // q*128 B is addressed correctly with base-offset 0 (the XOR uses absolute address bits);
@@ -72,13 +73,14 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t base_offs
   return d;
 }
 
+template <int NQ_T>   // compile-time bound of the Toeplitz block loop (3: K <= 129 undilated; 5: the general case)
 __global__ void __launch_bounds__(THREADS, 2)
 dw_tma_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + NSTAGE * A_STAGE;
-  uint8_t* sO = sB + NQ * BQ;
+  uint8_t* sO = sB + p.NQ * BQ;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sO + OUT_STAGE);
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* acc_full = empty_bar + NSTAGE;
@@ -128,7 +130,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
         const int s = n % NSTAGE;
         ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&full_bar[s], box_bytes);
-        tma_load_4d(sA + s * A_STAGE, &p.in, &full_bar[s], 0, -1, c, (tile0 + n) * p.NB);
+        tma_load_4d(sA + s * A_STAGE, &p.in, &full_bar[s], 0, -p.HL, c, (tile0 + n) * p.NB);
       }
     }
   } else if (warp == 1) {
@@ -136,7 +138,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(MROWS, L, 0, 0);
       const uint32_t sb = ptx::smem_u32(sB);
-      const int jlo = 64 - p.P, jhi = 127 + p.P;
+      const int jlo = 64 * p.HL - p.P, jhi = 64 * p.HL + 63 + p.P;  // non-zero band of the stacked Toeplitz rows
       ptx::mbar_wait(b_ready, 0);
       for (int n = 0; n < ntiles; ++n) {
         const int s = n % NSTAGE, a = n % ACC_STAGES;
@@ -146,7 +148,8 @@ dw_tma_kernel(const __grid_constant__ Params p) {
         const uint32_t sa = ptx::smem_u32(sA + s * A_STAGE);
         uint32_t acc = 0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
+        for (int q = 0; q < NQ_T; ++q) {
+          if (q >= p.NQ) break;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const int j0 = 64 * q + 16 * ks;
@@ -163,17 +166,24 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     }
   }
   if (warp >= 2) {
-    // ===== Toeplitz blocks of this channel: Tq[r][j] = w[64 q + j - 64 - r + P], SW128 rows of 128 B =====
+    // ===== Toeplitz blocks of this channel: Tq[r][j] = w[(64 q + j - 64 HL - r + P) / D], SW128 rows of 128 B =====
     const float* wc = p.w + (size_t)c * p.K;
-    for (int ci = tid - 64; ci < NQ * 64 * 8; ci += THREADS - 64) {
+    const int kd = p.K * p.D;
+    for (int ci = tid - 64; ci < p.NQ * 64 * 8; ci += THREADS - 64) {
       const int q = ci >> 9, r = (ci >> 3) & 63, g = ci & 7;
-      const int d0 = 64 * q + 8 * g - 64 - r + p.P;
+      const int d0 = 64 * q + 8 * g - 64 * p.HL - r + p.P;
       uint32_t pk[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         const int da = d0 + 2 * h, db = da + 1;
-        const float fa = (da >= 0 && da < p.K) ? wc[da] : 0.f;
-        const float fb = (db >= 0 && db < p.K) ? wc[db] : 0.f;
+        float fa, fb;
+        if (p.D == 1) {  // uniform branch: no integer division on the common path
+          fa = (da >= 0 && da < kd) ? wc[da] : 0.f;
+          fb = (db >= 0 && db < kd) ? wc[db] : 0.f;
+        } else {
+          fa = (da >= 0 && da < kd && da % p.D == 0) ? wc[da / p.D] : 0.f;
+          fb = (db >= 0 && db < kd && db % p.D == 0) ? wc[db / p.D] : 0.f;
+        }
         __nv_bfloat162 pr = __floats2bfloat162_rn(fa, fb);
         pk[h] = *reinterpret_cast<uint32_t*>(&pr);
       }
@@ -247,16 +257,20 @@ dw_tma_kernel(const __grid_constant__ Params p) {
 
 int option_dw_base_offset();
 
-int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
+int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st) {
-  if (!(K % 2 == 1 && P == K / 2 && K <= 129 && pitch_in == pitch_out && pitch_in % 64 == 0 && C <= 65535))
+  // stride 1, length preserving ("same") padding: 2 P == D (K - 1)
+  if (!(2 * P == D * (K - 1) && D >= 1 && pitch_in == pitch_out && pitch_in % 64 == 0 && C <= 65535))
     return TS_ERR_UNSUPPORTED;
   dwt2::Params p;
   memset(&p, 0, sizeof(p));
   p.w = w; p.lens = lens;
-  p.B = B; p.C = C; p.T = T; p.K = K; p.P = P;
+  p.B = B; p.C = C; p.T = T; p.K = K; p.P = P; p.D = D;
   p.W = pitch_in / 64;
-  p.R = p.W + 2;
+  p.HL = ceil_div(P, 64);
+  p.NQ = p.HL + 1 + (63 + P) / 64;
+  if (p.NQ > dwt2::MAX_NQ || P == 0) return TS_ERR_UNSUPPORTED;
+  p.R = p.W + p.NQ - 1;
   if (p.R > dwt2::MROWS) return TS_ERR_UNSUPPORTED;
   p.NB = dwt2::MROWS / p.R;
   if (p.NB > 256 || p.R > 256) return TS_ERR_UNSUPPORTED;
@@ -286,11 +300,17 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
   if ((rc = tma::encode(&p.out, y, 4, dims, strides, box)) != TS_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    TS_CUDA(cudaFuncSetAttribute(dwt2::dw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwt2::SMEM_BYTES));
+    TS_CUDA(cudaFuncSetAttribute(dwt2::dw_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dwt2::smem_bytes(3)));
+    TS_CUDA(cudaFuncSetAttribute(dwt2::dw_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dwt2::smem_bytes(dwt2::MAX_NQ)));
     attr_set = true;
   }
   dim3 grid(C, groups);
-  dwt2::dw_tma_kernel<<<grid, dwt2::THREADS, dwt2::SMEM_BYTES, st>>>(p);
+  if (p.NQ <= 3)
+    dwt2::dw_tma_kernel<3><<<grid, dwt2::THREADS, dwt2::smem_bytes(p.NQ), st>>>(p);
+  else
+    dwt2::dw_tma_kernel<5><<<grid, dwt2::THREADS, dwt2::smem_bytes(p.NQ), st>>>(p);
   TS_LAUNCH_CHECK("dw_tma_kernel");
   return TS_OK;
 }

@@ -56,33 +56,70 @@ __global__ void lengths_i32_to_i64_kernel(const int32_t* __restrict__ in, int64_
 // SqueezeExcite excitation (citrinet/blocks.py:77-83): gate[b, c] = sigmoid(W2 relu(W1 (pool[b, :] / T))).
 // One CTA per batch element; pool holds the per-channel SUMS over all T frames (no mask -- the reference pools
 // with AdaptiveAvgPool1d over the whole padded time axis).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 se_fc_kernel(const float* __restrict__ pool, float inv_T, const float* __restrict__ w1, const float* __restrict__ w2,
              int C, int H, float* __restrict__ gate) {
   extern __shared__ float sm[];
   float* mean = sm;        // [C]
   float* hid = sm + C;     // [H]
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(size_t)b * C + c] * inv_T;
   __syncthreads();
-  for (int h = warp; h < H; h += blockDim.x / 32) {
-    const float* wr = w1 + (size_t)h * C;
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(wr[c], mean[c], a);
-    a = warp_sum(a);
-    if (lane == 0) hid[h] = fmaxf(a, 0.f);
+  // hidden units: 4 rows of W1 per warp pass, 4 independent 128-byte loads per lane in flight
+  for (int h0 = warp * 4; h0 < H; h0 += nwarps * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < C; c += 32) {
+      const float mv = mean[c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (h0 + u < H) a[u] = fmaf(__ldg(w1 + (size_t)(h0 + u) * C + c), mv, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float r = warp_sum(a[u]);
+      if (lane == 0 && h0 + u < H) hid[h0 + u] = fmaxf(r, 0.f);
+    }
   }
   __syncthreads();
-  for (int c = warp; c < C; c += blockDim.x / 32) {
-    const float* wr = w2 + (size_t)c * H;
-    float a = 0.f;
-    for (int h = lane; h < H; h += 32) a = fmaf(wr[h], hid[h], a);
-    a = warp_sum(a);
-    if (lane == 0) gate[(size_t)b * C + c] = 1.f / (1.f + __expf(-a));
+  // gates: 4 rows of W2 per warp pass
+  for (int c0 = warp * 4; c0 < C; c0 += nwarps * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int h = lane; h < H; h += 32) {
+      const float hv = hid[h];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < C) a[u] = fmaf(__ldg(w2 + (size_t)(c0 + u) * H + h), hv, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float r = warp_sum(a[u]);
+      if (lane == 0 && c0 + u < C) gate[(size_t)b * C + c0 + u] = 1.f / (1.f + __expf(-r));
+    }
   }
 }
 
+// Strided 1x1 "conv" gather for residual branches with stride (citrinet/blocks.py:159-168): out[b, c, t'] =
+// x[b, c, S t'] for S t' < min(T_in, len_in[b]), else 0 (MaskedConv1d.mask_fill); pad frames zero.  8 outputs/thread.
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_in, int S,
+                                   const int32_t* __restrict__ len_in, __nv_bfloat16* __restrict__ y, int pitch_out,
+                                   long long rows) {
+  const long long row = blockIdx.x;
+  const int t0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t0 >= pitch_out) return;
+  int lin = T_in;
+  if (len_in != nullptr) lin = min(lin, max(len_in[row / C], 0));
+  const __nv_bfloat16* xr = x + row * pitch_in;
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int ta = (t0 + 2 * h) * S, tb = (t0 + 2 * h + 1) * S;
+    const unsigned short a = (ta < lin) ? *reinterpret_cast<const unsigned short*>(xr + ta) : (unsigned short)0;
+    const unsigned short b = (tb < lin) ? *reinterpret_cast<const unsigned short*>(xr + tb) : (unsigned short)0;
+    o[h] = (uint32_t)a | ((uint32_t)b << 16);
+  }
+  *reinterpret_cast<uint4*>(y + row * pitch_out + t0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
 
 // SE excite for blocks WITHOUT a residual branch (Citrinet stem / epilogue, citrinet/blocks.py:154,195-197):
 // out = relu(gate[b, c] * y1[b, c, t]), frames t >= lens[b] stored as zero when lens is given.  8 frames per thread.
@@ -115,49 +152,67 @@ __global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ y1, const floa
 // + popcount prefix sums.  Blanks are kept (the reference strips the blank *string* after joining) unless
 // drop_blank >= 0.
 template <typename InT>
-__global__ void __launch_bounds__(256)
-ctc_greedy_kernel(const InT* __restrict__ logits, int V, int T, int pitch, int64_t* __restrict__ ids,
-                  int64_t* __restrict__ collapsed, int32_t* __restrict__ counts, int drop_blank) {
-  extern __shared__ int s_ids[];
-  const int b = blockIdx.x;
-  const InT* base = logits + (size_t)b * V * pitch;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float best = ld_as_float(base + t);
-    int bi = 0;
-    bool best_nan = best != best;
-    for (int v = 1; v < V && !best_nan; ++v) {
-      const float x = ld_as_float(base + (size_t)v * pitch + t);
-      if (x != x) {
-        bi = v;
+__global__ void __launch_bounds__(128)
+ctc_argmax_kernel(const InT* __restrict__ logits, int V, int T, int pitch, int64_t* __restrict__ ids) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const InT* base = logits + (size_t)b * V * pitch + t;
+  float best = ld_as_float(base);
+  int bi = 0;
+  bool best_nan = best != best;
+  int v = 1;
+  for (; v + 4 <= V && !best_nan; v += 4) {   // 4 independent coalesced loads in flight
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = ld_as_float(base + (size_t)(v + u) * pitch);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (best_nan) break;
+      if (x[u] != x[u]) {
+        bi = v + u;
         best_nan = true;
-      } else if (x > best) {
-        best = x;
-        bi = v;
+      } else if (x[u] > best) {
+        best = x[u];
+        bi = v + u;
       }
     }
-    s_ids[t] = bi;
-    if (ids != nullptr) ids[(size_t)b * T + t] = bi;
   }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int n = 0;
-    for (int t0 = 0; t0 < T; t0 += 32) {
-      const int t = t0 + lane;
-      bool keep = false;
-      int id = -1;
-      if (t < T) {
-        id = s_ids[t];
-        keep = (t == 0) || (id != s_ids[t - 1]);
-        if (drop_blank >= 0 && id == drop_blank) keep = false;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) collapsed[(size_t)b * T + n + __popc(m & ((1u << lane) - 1u))] = id;
-      n += __popc(m);
+  for (; v < V && !best_nan; ++v) {
+    const float x = ld_as_float(base + (size_t)v * pitch);
+    if (x != x) {
+      bi = v;
+      best_nan = true;
+    } else if (x > best) {
+      best = x;
+      bi = v;
     }
-    for (int t = n + lane; t < T; t += 32) collapsed[(size_t)b * T + t] = -1;
-    if (lane == 0) counts[b] = n;
   }
+  ids[(size_t)b * T + t] = bi;
+}
+
+// one warp per utterance: collapse consecutive repeats with ballot + popcount prefix sums
+__global__ void __launch_bounds__(32)
+ctc_collapse_kernel(const int64_t* __restrict__ ids, int T, int64_t* __restrict__ collapsed,
+                    int32_t* __restrict__ counts, int drop_blank) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int64_t* row = ids + (size_t)b * T;
+  int n = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    int64_t id = -1;
+    if (t < T) {
+      id = row[t];
+      keep = (t == 0) || (id != row[t - 1]);
+      if (drop_blank >= 0 && id == drop_blank) keep = false;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) collapsed[(size_t)b * T + n + __popc(m & ((1u << lane) - 1u))] = id;
+    n += __popc(m);
+  }
+  for (int t = n + lane; t < T; t += 32) collapsed[(size_t)b * T + t] = -1;
+  if (lane == 0) counts[b] = n;
 }
 
 }  // namespace misc
@@ -220,30 +275,43 @@ extern "C" int ts_se_fc(const float* pool, int B, int C, int H, int T, const flo
   TS_REQUIRE(B > 0 && C > 0 && H > 0 && T > 0, TS_ERR_INVALID, "ts_se_fc: bad sizes");
   const size_t smem = (size_t)(C + H) * sizeof(float);
   TS_REQUIRE(smem <= 48 * 1024, TS_ERR_UNSUPPORTED, "ts_se_fc: C=%d too large", C);
-  misc::se_fc_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, w2, C, H, gate);
+  misc::se_fc_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, w2, C, H, gate);
   TS_LAUNCH_CHECK("se_fc_kernel");
   return TS_OK;
 }
 
 extern "C" int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch, int64_t* ids,
                              int64_t* collapsed, int32_t* counts, int drop_blank, void* stream) {
-  TS_REQUIRE(logits && collapsed && counts, TS_ERR_INVALID, "ts_ctc_greedy: null pointer");
-  TS_REQUIRE(B > 0 && V > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_ctc_greedy: bad sizes");
-  const size_t smem = (size_t)T * sizeof(int);
-  TS_REQUIRE(smem <= 200 * 1024, TS_ERR_UNSUPPORTED, "ts_ctc_greedy: T=%d too long for one CTA", T);
+  TS_REQUIRE(logits && ids && collapsed && counts, TS_ERR_INVALID, "ts_ctc_greedy: null pointer");
+  TS_REQUIRE(B > 0 && V > 0 && T > 0 && pitch >= T && B <= 65535, TS_ERR_INVALID, "ts_ctc_greedy: bad sizes");
+  dim3 grid(ceil_div(T, 128), B);
   if (dtype == TS_F32) {
-    auto k = misc::ctc_greedy_kernel<float>;
-    if (smem > 48 * 1024) TS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<B, 256, smem, (cudaStream_t)stream>>>((const float*)logits, V, T, pitch, ids, collapsed, counts, drop_blank);
+    misc::ctc_argmax_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)logits, V, T, pitch, ids);
   } else if (dtype == TS_BF16) {
-    auto k = misc::ctc_greedy_kernel<__nv_bfloat16>;
-    if (smem > 48 * 1024) TS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<B, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, V, T, pitch, ids, collapsed, counts,
-                                              drop_blank);
+    misc::ctc_argmax_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, V, T,
+                                                                                 pitch, ids);
   } else {
     TS_REQUIRE(false, TS_ERR_INVALID, "ts_ctc_greedy: bad dtype %d", dtype);
   }
-  TS_LAUNCH_CHECK("ctc_greedy_kernel");
+  TS_LAUNCH_CHECK("ctc_argmax_kernel");
+  misc::ctc_collapse_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(ids, T, collapsed, counts, drop_blank);
+  TS_LAUNCH_CHECK("ctc_collapse_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_in, int S, const int32_t* len_in,
+                              void* y, int pitch_out, void* stream) {
+  TS_REQUIRE(x && y, TS_ERR_INVALID, "ts_gather_rows: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T_in > 0 && S > 0 && pitch_in >= T_in && pitch_out % 8 == 0, TS_ERR_INVALID,
+             "ts_gather_rows: bad sizes");
+  const int T_out = (T_in - 1) / S + 1;
+  TS_REQUIRE(pitch_out >= T_out, TS_ERR_INVALID, "ts_gather_rows: pitch_out %d < T_out %d", pitch_out, T_out);
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_gather_rows: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch_out / 8, 128));
+  misc::gather_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, T_in, pitch_in, S, len_in,
+                                                                   (__nv_bfloat16*)y, pitch_out, rows);
+  TS_LAUNCH_CHECK("gather_rows_kernel");
   return TS_OK;
 }
 

@@ -155,7 +155,7 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
         if plan.res_w is not None:
             xr = x_in
             if plan.res_stride > 1:  # 1x1 conv with stride: gather every stride-th (masked) input frame
-                xr = ops.dw_conv(x_in, T_in, plan.ones, plan.res_stride, 1, 0, lens_in, True)
+                xr = ops.gather_rows(x_in, T_in, plan.res_stride, lens_in)
         if plan.se_w1 is None:
             if xr is not None:
                 out = ops.pw_gemm(sb.pw_w, a, plan.res_w, xr, Ta, plan.total_shift, out_lens, False, True, None, None,

@@ -286,3 +286,21 @@ def conv_lengths(lens: Tensor, kernel_size: int, stride: int, dilation: int, pad
 @conv_lengths.register_fake
 def _(lens, kernel_size, stride, dilation, padding):
     return torch.empty_like(lens)
+
+
+@torch.library.custom_op(f"{NS}::gather_rows", mutates_args=())
+def gather_rows(x: Tensor, T_in: int, stride: int, lens: Optional[Tensor]) -> Tensor:
+    """``y[b,c,t'] = x[b,c,stride*t']`` over bf16 rows, masked by the INPUT lengths: the input side of a strided
+    1x1 residual conv."""
+    _need_cuda(x)
+    B, C, pitch = x.shape
+    T_out = (T_in - 1) // stride + 1
+    out = torch.empty((B, C, row_pitch(T_out)), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ts_gather_rows(_ptr(x), B, C, T_in, pitch, stride, _ptr(lens) if lens is not None else None,
+                                         _ptr(out), out.shape[2], _stream()), "ts_gather_rows")
+    return out
+
+
+@gather_rows.register_fake
+def _(x, T_in, stride, lens):
+    return x.new_empty((x.shape[0], x.shape[1], row_pitch((T_in - 1) // stride + 1)))

@@ -96,10 +96,15 @@ class ModelWorkload:
     def roofline(self, steps):
         """Eager pass with CUDA events around every kernel launch; reports the kernel class with the largest
         share of the step against its own roofline (HBM for depthwise, tensor for the GEMMs)."""
-        ops.PROFILE = []
         n = max(2, min(steps, 3))
+        self.model.predict_ids(self.audio[0])
+        torch.cuda.synchronize()
+        ops.PROFILE = []
         try:
             for i in range(n):
+                # keep the GPU busy while the CPU queues the ~160-300 launches of this pass, otherwise every
+                # event pair would also time the host-side launch latency (the eager path is CPU-bound)
+                torch.cuda._sleep(int(40e6))
                 self.model.predict_ids(self.audio[i % self.NBUF])
             torch.cuda.synchronize()
             recs = ops.PROFILE
