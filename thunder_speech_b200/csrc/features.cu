@@ -20,49 +20,62 @@ constexpr int NFFT = 512;
 constexpr int NBINS = NFFT / 2 + 1;
 constexpr int FT = 32;       // frames per CTA
 constexpr int NWARPS = 8;    // 256 threads; each warp transforms FT / NWARPS = 4 frames (2 packed pairs)
-constexpr int XBUF = 576;    // floats per exchange array (max index 72*7+63 = 567)
+constexpr int XBUF = 576;    // float2 elements per warp exchange buffer (max index 72*7+63 = 567)
 constexpr int XS1 = 72;      // exchange 1: idx = 72*k2 + 8*n1 + n0
-constexpr int XS0 = 68;      // exchange 2: idx = 68*n0 + 8*k1 + k2
+constexpr int XS0 = 66;      // exchange 2: idx = 66*n0 + 8*k1 + k2 (float2 elements: distinct mod 16 per half-warp)
 constexpr int TILE_LD = FT + 1;
 constexpr int MAX_NNZ = 2048;
 constexpr int MAX_NFILT = 128;
 
 struct SmemLayout {
-  int ybuf, tw_re, tw_im, win, mstart, mcount, moff, mw, xch, tile, total;
+  int raw, raw_stride, tw, mstart, mcount, moff, mw, xch, tile, total;   // offsets in floats
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int hop, int nfilt, int nnz) {
   SmemLayout L;
   int o = 0;
-  L.ybuf = o;   o += ((FT - 1) * hop + NFFT + 3) & ~3;
-  L.tw_re = o;  o += NFFT;
-  L.tw_im = o;  o += NFFT;
-  L.win = o;    o += NFFT;
+  L.raw_stride = ((FT - 1) * hop + NFFT + 8 + 3) & ~3;   // span + previous sample + alignment slack
+  L.raw = o;    o += 2 * L.raw_stride;                   // double buffered
+  L.tw = o;     o += 2 * NFFT;                            // float2
   L.mstart = o; o += (nfilt + 3) & ~3;
   L.mcount = o; o += (nfilt + 3) & ~3;
   L.moff = o;   o += (nfilt + 3) & ~3;
   L.mw = o;     o += (nnz + 3) & ~3;
-  L.xch = o;    o += NWARPS * 2 * XBUF;
+  L.xch = o;    o += NWARPS * 2 * XBUF;                   // float2 per warp
   L.tile = o;   o += nfilt * TILE_LD;
   L.total = o;
   return L;
 }
 
-// kCentre320: window support is [96, 416) (win_length 320 centred in 512) => only FFT input slots
-// q in [3, 12] (n = lane + 32 q) are non-zero for every lane, the rest are compile-time zeros.
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent kernel: each CTA loops over (utterance, 32-frame tile) work items.  The raw audio span of the NEXT item is
+// fetched with cp.async into the other half of a double buffer while the current item is transformed.
+//
+// Buffer semantics: interior items hold RAW samples v[i] = x[a0 + i] and the pre-emphasis is folded into the window
+// multiply ( w[n]*(x[n] - p*x[n-1]) = w[n]*v[n] - (p*w[n])*v[n-1] ); items that touch a row boundary (reflect padding,
+// y[0] = x[0]) are filled synchronously with the already pre-emphasised, reflected samples and use p_eff = 0.
+//
+// kCentre320: window support is inside [96, 416) (win_length 320 centred in 512) => only FFT input slots q in [3, 12]
+// (n = lane + 32 q) are non-zero for every lane, the rest are compile-time zeros.
 template <bool kCentre320>
 __global__ void __launch_bounds__(NWARPS * 32, 2)
-logmel_kernel(const float* __restrict__ audio, int N, int F, int hop, float preemph,
+logmel_kernel(const float* __restrict__ audio, int B, int N, int F, int hop, float preemph,
               const float* __restrict__ window_full, const float2* __restrict__ twiddle,
               const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
               const int32_t* __restrict__ mel_off, const float* __restrict__ mel_w, int nfilt, int nnz,
-              float* __restrict__ logmel) {
+              float* __restrict__ logmel, int tiles_per_row, int num_items) {
   extern __shared__ __align__(16) float smem[];
   const SmemLayout L = smem_layout(hop, nfilt, nnz);
-  float* ybuf = smem + L.ybuf;
-  float* tw_re = smem + L.tw_re;
-  float* tw_im = smem + L.tw_im;
-  float* win = smem + L.win;
+  float2* tw = reinterpret_cast<float2*>(smem + L.tw);
   int* s_mstart = reinterpret_cast<int*>(smem + L.mstart);
   int* s_mcount = reinterpret_cast<int*>(smem + L.mcount);
   int* s_moff = reinterpret_cast<int*>(smem + L.moff);
@@ -72,178 +85,207 @@ logmel_kernel(const float* __restrict__ audio, int N, int F, int hop, float pree
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int b = blockIdx.y;
-  const int f0 = blockIdx.x * FT;
-  const float* x = audio + (size_t)b * N;
+  float2* xch = reinterpret_cast<float2*>(smem + L.xch) + warp * XBUF;
 
-  // ---- stage tables and the pre-emphasised, reflect-padded audio span of this frame tile -------------
-  for (int i = tid; i < NFFT; i += NWARPS * 32) {
-    float2 t = twiddle[i];
-    tw_re[i] = t.x;
-    tw_im[i] = t.y;
-    win[i] = window_full[i];
-  }
+  // ---- per-CTA tables; per-lane window taps (and preemph * taps) in registers ----------------------------
+  for (int i = tid; i < NFFT; i += NWARPS * 32) tw[i] = twiddle[i];
   for (int i = tid; i < nfilt; i += NWARPS * 32) {
     s_mstart[i] = mel_start[i];
     s_mcount[i] = mel_count[i];
     s_moff[i] = mel_off[i];
   }
   for (int i = tid; i < nnz; i += NWARPS * 32) s_mw[i] = mel_w[i];
-
-  const int span = (FT - 1) * hop + NFFT;
-  const int s0 = f0 * hop - NFFT / 2;
-  for (int i = tid; i < span; i += NWARPS * 32) {
-    int s = s0 + i;
-    float v = 0.f;
-    if (s > -NFFT / 2 - 1 && s < N + NFFT / 2) {
-      int r = s < 0 ? -s : (s >= N ? 2 * (N - 1) - s : s);  // reflect (torch.stft center=True)
-      // y[0] = x[0]; y[n] = x[n] - preemph * x[n-1]   (PreEmphasisFilter over the whole padded row)
-      v = (r >= 1) ? (x[r] - preemph * x[r - 1]) : x[0];
-    }
-    ybuf[i] = v;
+  constexpr int Q0 = kCentre320 ? 3 : 0, Q1 = kCentre320 ? 13 : 16;
+  float wq[Q1 - Q0], wpq[Q1 - Q0];
+#pragma unroll
+  for (int q = Q0; q < Q1; ++q) {
+    wq[q - Q0] = window_full[lane + 32 * q];
+    wpq[q - Q0] = preemph * wq[q - Q0];
   }
-  __syncthreads();
+  // per-lane twiddles of pass 1: W64^{n1 k2}, n1 = lane/8 + 4h (k2 = 0 is 1)
+  const int n0 = lane & 7;
+  const int span = (FT - 1) * hop + NFFT;     // samples of one item (without the "previous sample")
+  const bool vec_ok = (N % 4 == 0) && (hop % 4 == 0);
 
-  float* xre = smem + L.xch + warp * 2 * XBUF;
-  float* xim = xre + XBUF;
+  // item -> (b, f0); fill buffer `buf` for item; returns p_eff selector through smem flag
+  __shared__ int s_boundary[2];
+  auto stage_item = [&](int item, int buf) {
+    const int b = item / tiles_per_row, f0 = (item - b * tiles_per_row) * FT;
+    const float* x = audio + (size_t)b * N;
+    const int s0 = f0 * hop - NFFT / 2;       // signal index of frame f0's sample 0
+    float* raw = smem + L.raw + buf * L.raw_stride;
+    // layout: raw[4 + i] <-> signal index s0 + i  (i = -1 is the previous sample); 4 floats of slack keep 16 B alignment
+    const bool interior = (s0 - 4 >= 0) && (s0 + span + 4 <= N);
+    if (interior) {
+      if (tid == 0) s_boundary[buf] = 0;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw);
+      if (vec_ok) {  // s0 % 4 == 0: copy [s0 - 4, s0 + span + 4) as 16-byte chunks
+        const float* src = x + s0 - 4;
+        for (int i = tid; i < (span + 8) / 4; i += NWARPS * 32) cp_async_16(dst + 16 * i, src + 4 * i);
+      } else {
+        const float* src = x + s0 - 4;
+        for (int i = tid + 3; i < span + 4; i += NWARPS * 32) cp_async_4(dst + 4 * i, src + i);
+      }
+    } else {
+      if (tid == 0) s_boundary[buf] = 1;
+      if (tid < 4) raw[tid] = 0.f;   // the "previous sample" slot is multiplied by p_eff = 0: keep it finite
+      for (int i = tid; i < span; i += NWARPS * 32) {
+        const int s = s0 + i;
+        float v = 0.f;
+        if (s > -NFFT / 2 - 1 && s < N + NFFT / 2) {
+          const int r = s < 0 ? -s : (s >= N ? 2 * (N - 1) - s : s);  // reflect (torch.stft center=True)
+          v = (r >= 1) ? (x[r] - preemph * x[r - 1]) : x[0];          // y[0] = x[0]
+        }
+        raw[4 + i] = v;
+      }
+    }
+    cp_async_commit();
+  };
 
-  constexpr int PAIRS_PER_WARP = FT / NWARPS / 2;
+  int item = blockIdx.x;
+  if (item < num_items) stage_item(item, 0);
+  for (int it = 0; item < num_items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = item + gridDim.x;
+    if (next < num_items) {
+      stage_item(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // buffer `buf` (and, first time, the tables) visible; previous item's tile rows written out
+    const int b = item / tiles_per_row, f0 = (item - b * tiles_per_row) * FT;
+    const float* raw = smem + L.raw + buf * L.raw_stride + 4;
+    const float pe = s_boundary[buf] ? 0.f : 1.f;
+
+    constexpr int PAIRS_PER_WARP = FT / NWARPS / 2;
 #pragma unroll 1
-  for (int p = 0; p < PAIRS_PER_WARP; ++p) {
-    const int fl1 = (warp * PAIRS_PER_WARP + p) * 2;  // local frame indices fl1, fl1 + 1
-    if (f0 + fl1 >= F) break;                        // warp-uniform
-    const float* y1 = ybuf + fl1 * hop;
-    const float* y2 = y1 + hop;
+    for (int pp = 0; pp < PAIRS_PER_WARP; ++pp) {
+      const int fl1 = (warp * PAIRS_PER_WARP + pp) * 2;  // local frame indices fl1, fl1 + 1
+      if (f0 + fl1 >= F) break;                          // warp-uniform
+      const float* y1 = raw + fl1 * hop;
+      const float* y2 = y1 + hop;
 
-    float ar[2][8], ai[2][8];
-    // ---- pass 1: butterflies g = lane + 32 h = n0 + 8 n1, inputs n = g + 64 n2 ----------------------
+      float ar[2][8], ai[2][8];
+      // ---- pass 1: butterflies g = lane + 32 h = n0 + 8 n1, inputs n = g + 64 n2 -----------------------
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
-        const int q = h + 2 * n2;
-        if (kCentre320 && (q < 3 || q > 12)) {
-          ar[h][n2] = 0.f;
-          ai[h][n2] = 0.f;
-        } else {
-          const int n = lane + 32 * q;
-          const float w = win[n];
-          ar[h][n2] = w * y1[n];
-          ai[h][n2] = w * y2[n];
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const int q = h + 2 * n2;
+          if (q < Q0 || q >= Q1) {
+            ar[h][n2] = 0.f;
+            ai[h][n2] = 0.f;
+          } else {
+            const int n = lane + 32 * q;
+            const float w = wq[q - Q0], wp = pe * wpq[q - Q0];
+            ar[h][n2] = fmaf(-wp, y1[n - 1], w * y1[n]);
+            ai[h][n2] = fmaf(-wp, y2[n - 1], w * y2[n]);
+          }
+        }
+        dft8(ar[h], ai[h]);
+        const int n1 = (lane >> 3) + 4 * h;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {  // twiddle W64^{n1 k2} = W512^{8 n1 k2}
+          float r = ar[h][k2], i = ai[h][k2];
+          if (k2 > 0) {
+            const float2 t = tw[8 * n1 * k2];
+            const float rr = r * t.x - i * t.y;
+            i = r * t.y + i * t.x;
+            r = rr;
+          }
+          xch[XS1 * k2 + lane + 32 * h] = make_float2(r, i);
         }
       }
-      dft8(ar[h], ai[h]);
-      const int n1 = (lane >> 3) + 4 * h;
+      __syncwarp();
+      // ---- pass 2: (n0 = lane % 8, k2 = lane / 8 + 4 h), sum over n1 -----------------------------------
 #pragma unroll
-      for (int k2 = 1; k2 < 8; ++k2) {  // twiddle W64^{n1 k2} = W512^{8 n1 k2}
-        const int e = 8 * n1 * k2;
-        const float c = tw_re[e], s = tw_im[e];
-        const float r = ar[h][k2], i = ai[h][k2];
-        ar[h][k2] = r * c - i * s;
-        ai[h][k2] = r * s + i * c;
-      }
+      for (int h = 0; h < 2; ++h) {
+        const int k2 = (lane >> 3) + 4 * h;
 #pragma unroll
-      for (int k2 = 0; k2 < 8; ++k2) {
-        xre[XS1 * k2 + lane + 32 * h] = ar[h][k2];
-        xim[XS1 * k2 + lane + 32 * h] = ai[h][k2];
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const float2 v = xch[XS1 * k2 + 8 * n1 + n0];
+          ar[h][n1] = v.x;
+          ai[h][n1] = v.y;
+        }
       }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k2 = (lane >> 3) + 4 * h;
+        dft8(ar[h], ai[h]);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {  // twiddle W512^{n0 (k2 + 8 k1)}
+          const float2 t = tw[n0 * (k2 + 8 * k1)];
+          const float r = ar[h][k1], i = ai[h][k1];
+          xch[XS0 * n0 + 8 * k1 + k2] = make_float2(r * t.x - i * t.y, r * t.y + i * t.x);
+        }
+      }
+      __syncwarp();
+      // ---- pass 3: j = lane + 32 h = k2 + 8 k1, sum over n0, output Z[j + 64 k0] -----------------------
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+#pragma unroll
+        for (int m0 = 0; m0 < 8; ++m0) {
+          const float2 v = xch[XS0 * m0 + j];
+          ar[h][m0] = v.x;
+          ai[h][m0] = v.y;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        dft8(ar[h], ai[h]);
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0) xch[j + 64 * k0] = make_float2(ar[h][k0], ai[h][k0]);
+      }
+      __syncwarp();
+      // ---- un-pack the two real spectra and take |.|^2 (sqrt then square, transform.py:205-207) -------
+      float2 pw[9];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const int k = lane + 32 * m;
+        pw[m] = make_float2(0.f, 0.f);
+        if (k < NBINS) {
+          const float2 z = xch[k], c = xch[(NFFT - k) & (NFFT - 1)];
+          const float r1 = 0.5f * (z.x + c.x), i1 = 0.5f * (z.y - c.y);
+          const float r2 = 0.5f * (z.y + c.y), i2 = 0.5f * (c.x - z.x);
+          const float m1 = sqrtf(r1 * r1 + i1 * i1);
+          const float m2 = sqrtf(r2 * r2 + i2 * i2);
+          pw[m] = make_float2(m1 * m1, m2 * m2);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const int k = lane + 32 * m;
+        if (k < NBINS) xch[k] = pw[m];
+      }
+      __syncwarp();
+      // ---- sparse mel projection + log (transform.py:250-254), both frames per shared-memory read ------
+      for (int m = lane; m < nfilt; m += 32) {
+        const int st = s_mstart[m], cnt = s_mcount[m], off = s_moff[m];
+        float a1 = 0.f, a2 = 0.f;
+        for (int j = 0; j < cnt; ++j) {
+          const float w = s_mw[off + j];
+          const float2 pv = xch[st + j];
+          a1 = fmaf(w, pv.x, a1);
+          a2 = fmaf(w, pv.y, a2);
+        }
+        tile[m * TILE_LD + fl1] = logf(a1 + 5.9604644775390625e-08f);  // 2^-24
+        tile[m * TILE_LD + fl1 + 1] = logf(a2 + 5.9604644775390625e-08f);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- pass 2: (n0 = lane % 8, k2 = lane / 8 + 4 h), sum over n1 ----------------------------------
-    const int n0 = lane & 7;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k2 = (lane >> 3) + 4 * h;
-#pragma unroll
-      for (int n1 = 0; n1 < 8; ++n1) {
-        ar[h][n1] = xre[XS1 * k2 + 8 * n1 + n0];
-        ai[h][n1] = xim[XS1 * k2 + 8 * n1 + n0];
-      }
+    __syncthreads();
+    // ---- coalesced write-out: one (filter) row segment of FT frames per warp instruction -------------
+    for (int m = warp; m < nfilt; m += NWARPS) {
+      const int f = f0 + lane;
+      if (lane < FT && f < F) logmel[((size_t)b * nfilt + m) * F + f] = tile[m * TILE_LD + lane];
     }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k2 = (lane >> 3) + 4 * h;
-      dft8(ar[h], ai[h]);
-#pragma unroll
-      for (int k1 = 0; k1 < 8; ++k1) {  // twiddle W512^{n0 (k2 + 8 k1)}
-        const int e = n0 * (k2 + 8 * k1);
-        const float c = tw_re[e], s = tw_im[e];
-        const float r = ar[h][k1], i = ai[h][k1];
-        xre[XS0 * n0 + 8 * k1 + k2] = r * c - i * s;
-        xim[XS0 * n0 + 8 * k1 + k2] = r * s + i * c;
-      }
-    }
-    __syncwarp();
-    // ---- pass 3: j = lane + 32 h = k2 + 8 k1, sum over n0, output Z[j + 64 k0] ----------------------
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;
-#pragma unroll
-      for (int m0 = 0; m0 < 8; ++m0) {
-        ar[h][m0] = xre[XS0 * m0 + j];
-        ai[h][m0] = xim[XS0 * m0 + j];
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;
-      dft8(ar[h], ai[h]);
-#pragma unroll
-      for (int k0 = 0; k0 < 8; ++k0) {
-        xre[j + 64 * k0] = ar[h][k0];
-        xim[j + 64 * k0] = ai[h][k0];
-      }
-    }
-    __syncwarp();
-    // ---- un-pack the two real spectra and take |.|^2 (sqrt then square, transform.py:205-207) ------
-    float p1[9], p2[9];
-#pragma unroll
-    for (int m = 0; m < 9; ++m) {
-      const int k = lane + 32 * m;
-      p1[m] = 0.f;
-      p2[m] = 0.f;
-      if (k < NBINS) {
-        const int kk = (NFFT - k) & (NFFT - 1);
-        const float zr = xre[k], zi = xim[k], cr = xre[kk], ci = xim[kk];
-        const float r1 = 0.5f * (zr + cr), i1 = 0.5f * (zi - ci);
-        const float r2 = 0.5f * (zi + ci), i2 = 0.5f * (cr - zr);
-        const float m1 = sqrtf(r1 * r1 + i1 * i1);
-        const float m2 = sqrtf(r2 * r2 + i2 * i2);
-        p1[m] = m1 * m1;
-        p2[m] = m2 * m2;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < 9; ++m) {
-      const int k = lane + 32 * m;
-      if (k < NBINS) {
-        xre[k] = p1[m];
-        xim[k] = p2[m];
-      }
-    }
-    __syncwarp();
-    // ---- sparse mel projection + log (transform.py:250-254) -----------------------------------------
-    for (int m = lane; m < nfilt; m += 32) {
-      const int st = s_mstart[m], cnt = s_mcount[m], off = s_moff[m];
-      float a1 = 0.f, a2 = 0.f;
-      for (int j = 0; j < cnt; ++j) {
-        const float w = s_mw[off + j];
-        a1 = fmaf(w, xre[st + j], a1);
-        a2 = fmaf(w, xim[st + j], a2);
-      }
-      tile[m * TILE_LD + fl1] = logf(a1 + 5.9604644775390625e-08f);  // 2^-24
-      tile[m * TILE_LD + fl1 + 1] = logf(a2 + 5.9604644775390625e-08f);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  // ---- coalesced write-out: one (filter) row segment of FT frames per warp instruction -------------
-  for (int m = warp; m < nfilt; m += NWARPS) {
-    const int f = f0 + lane;
-    if (lane < FT && f < F) logmel[((size_t)b * nfilt + m) * F + f] = tile[m * TILE_LD + lane];
+    // the next iteration's first __syncthreads orders these tile reads before the next item's tile writes
   }
 }
 
@@ -335,21 +377,30 @@ extern "C" int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, f
   TS_REQUIRE(nfilt <= feat::MAX_NFILT && nnz <= feat::MAX_NNZ, TS_ERR_UNSUPPORTED,
              "ts_logmel: filter bank too dense (nfilt=%d nnz=%d, limits %d/%d)", nfilt, nnz, feat::MAX_NFILT,
              feat::MAX_NNZ);
-  TS_REQUIRE(B <= 65535, TS_ERR_UNSUPPORTED, "ts_logmel: B=%d > 65535", B);
   const int F = 1 + N / hop;
   const feat::SmemLayout L = feat::smem_layout(hop, nfilt, nnz);
   const size_t smem = (size_t)L.total * sizeof(float);
-  TS_REQUIRE(smem <= 227 * 1024, TS_ERR_UNSUPPORTED, "ts_logmel: hop=%d needs %zu bytes of shared memory", hop, smem);
+  TS_REQUIRE(smem <= 113 * 1024, TS_ERR_UNSUPPORTED, "ts_logmel: hop=%d needs %zu bytes of shared memory", hop, smem);
   TS_REQUIRE(0 <= win_lo && win_lo < win_hi && win_hi <= n_fft, TS_ERR_INVALID, "ts_logmel: bad window support [%d,%d)",
              win_lo, win_hi);
   // sparse-input FFT when the window support is inside [96, 416) (the reference default: 320 centred in 512)
   const bool centre320 = win_lo >= 96 && win_hi <= 416;
   auto kern = centre320 ? feat::logmel_kernel<true> : feat::logmel_kernel<false>;
   TS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(F, feat::FT), B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    TS_CUDA(cudaGetDevice(&dev));
+    TS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles_per_row = ceil_div(F, feat::FT);
+  const long long items_ll = (long long)B * tiles_per_row;
+  TS_REQUIRE(items_ll < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_logmel: too many frame tiles");
+  const int num_items = (int)items_ll;
+  const int grid = num_items < 2 * num_sms ? num_items : 2 * num_sms;
   kern<<<grid, feat::NWARPS * 32, smem, (cudaStream_t)stream>>>(
-      audio, N, F, hop, preemph, window_full, reinterpret_cast<const float2*>(twiddle), mel_start, mel_count,
-      mel_off, mel_w, nfilt, nnz, logmel);
+      audio, B, N, F, hop, preemph, window_full, reinterpret_cast<const float2*>(twiddle), mel_start, mel_count,
+      mel_off, mel_w, nfilt, nnz, logmel, tiles_per_row, num_items);
   TS_LAUNCH_CHECK("logmel_kernel");
   return TS_OK;
 }

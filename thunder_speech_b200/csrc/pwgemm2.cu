@@ -17,6 +17,7 @@
 #include "tma_host.cuh"
 
 namespace ts {
+int option_pw_bn();
 namespace pw2 {
 
 constexpr int BM = 256, BK = 64, UMMA_K = 16;
@@ -51,6 +52,7 @@ struct Params {
   const float* se_scale;
   const __nv_bfloat16* y1;
   int y1_pitch;
+  int debug_no_loads;   // experiment: the producer signals the stages full without issuing any TMA load
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -118,11 +120,31 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
       const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
       const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
       const int m0 = mt * BM, t0 = nt * BN;
+      // pull the NEXT tile's activation boxes into L2 now (DRAM -> L2 overlaps this tile's main loop), so that its
+      // TMA loads see L2-hit latency and the 3-4 shared-memory stages suffice to keep the tensor pipe fed
+      {
+        const int ntile = tile + gridDim.x;
+        if (ntile < p.num_tiles) {
+          const int nrest = ntile / p.m_tiles;
+          const int nnt = nrest % p.n_tiles, nb = nrest / p.n_tiles;
+          for (int kc = 0; kc < num_k; ++kc) {
+            const bool seg1 = kc >= p.kc0;
+            const CUtensorMap* mb = seg1 ? &p.b1 : &p.b0;
+            const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) ptx::tma_prefetch_3d(mb, nnt * BN + 64 * j, k0, nb);
+          }
+        }
+      }
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
         const int s = cnt % STAGES;
         ptx::mbar_wait(&empty_bar[s], ((cnt / STAGES) & 1) ^ 1);
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
+        if (p.debug_no_loads) {
+          ptx::mbar_arrive(&full_bar[s]);
+          continue;
+        }
         ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         const bool seg1 = kc >= p.kc0;
         const CUtensorMap* ma = seg1 ? &p.a1 : &p.a0;
@@ -274,7 +296,9 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
   memset(&p, 0, sizeof(p));
   int rc;
   // tile width: 256 frames for tensor-bound (K >= 1024) GEMMs, 128 with double-buffered accumulators otherwise
-  const int BN = (cin0 + cin1 >= 1024) ? 256 : 128;
+  int BN = (cin0 + cin1 >= 1024) ? 256 : 128;
+  if ((option_pw_bn() & 0x1ff) == 128 || (option_pw_bn() & 0x1ff) == 256) BN = option_pw_bn() & 0x1ff;  // experiment
+  p.debug_no_loads = (option_pw_bn() & 0x1000) ? 1 : 0;
   if ((rc = tma::make_2d_bf16(&p.a0, w0, cin0, Cout, (uint64_t)cin0 * 2, pw2::BK, pw2::BM)) != TS_OK) return rc;
   if ((rc = tma::make_3d_bf16(&p.b0, x0, T, cin0, B, (uint64_t)x0_pitch * 2, (uint64_t)cin0 * x0_pitch * 2, 64, pw2::BK,
                               1)) != TS_OK)

@@ -13,11 +13,13 @@ def dft8(v):  # v[8] -> DFT_8
     return np.array([(v * W(8, k * kk)).sum() for kk in range(8)])
 
 def banks_ok(idx_by_lane):
-    b = np.array(idx_by_lane) % 32
-    return len(set(b.tolist())) == len(b)
+    # 8-byte (float2) elements: a warp access is served as two half-warp wavefronts; conflict free iff the 16 lanes of
+    # each half hit 16 distinct 8-byte bank pairs (idx mod 16)
+    idx = np.array(idx_by_lane)
+    return all(len(set((idx[h * 16:(h + 1) * 16] % 16).tolist())) == 16 for h in range(2))
 
 S1 = 72   # exchange-1 layout: idx = 72*k2 + 8*n1 + n0
-S0 = 68   # exchange-2 layout: idx = 68*n0 + 8*k1 + k2
+S0 = 66   # exchange-2 layout: idx = 66*n0 + 8*k1 + k2 (float2 elements)
 buf = np.zeros(576, complex)
 
 # ---- stage 1: lane l, half h: butterfly g = l + 32h = n0 + 8 n1 ; inputs z[g + 64 n2]
