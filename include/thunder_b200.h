@@ -107,9 +107,10 @@ int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const voi
 
 /* ---- (4) SqueezeExcite FC, greedy CTC ------------------------------------------------------- */
 /* gate[b, :] = sigmoid(W2 relu(W1 (pool[b, :] / T)))  -- SqueezeExcite.fc + sigmoid (citrinet/blocks.py:63-83).
- *   pool [B, C] f32 sums over all T frames, w1 [H, C] f32, w2 [C, H] f32 (nn.Linear layouts, no bias) */
-int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* gate,
-             void* stream);
+ *   pool [B, C] f32 sums over all T frames, w1 [H, C] f32, w2 [C, H] f32 (nn.Linear layouts, no bias),
+ *   hid [B, H] f32 scratch (the ReLU'd hidden layer), gate [B, C] f32 out */
+int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* hid,
+             float* gate, void* stream);
 
 /* out = relu(gate[b, c] * y1[b, c, t]) over bf16 rows: SqueezeExcite scale + `mout` ReLU for blocks without a
  * residual branch (citrinet/blocks.py:154,195-197); frames t >= lens[b] are stored as zero when lens != NULL */

@@ -56,46 +56,57 @@ __global__ void lengths_i32_to_i64_kernel(const int32_t* __restrict__ in, int64_
 // SqueezeExcite excitation (citrinet/blocks.py:77-83): gate[b, c] = sigmoid(W2 relu(W1 (pool[b, :] / T))).
 // One CTA per batch element; pool holds the per-channel SUMS over all T frames (no mask -- the reference pools
 // with AdaptiveAvgPool1d over the whole padded time axis).
-__global__ void __launch_bounds__(512)
-se_fc_kernel(const float* __restrict__ pool, float inv_T, const float* __restrict__ w1, const float* __restrict__ w2,
-             int C, int H, float* __restrict__ gate) {
-  extern __shared__ float sm[];
-  float* mean = sm;        // [C]
-  float* hid = sm + C;     // [H]
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(size_t)b * C + c] * inv_T;
+// Two kernels so that both FCs spread over (units / 16) x B CTAs instead of one CTA per utterance:
+//   se_hidden_kernel: hid[b, h] = relu(sum_c W1[h, c] * pool[b, c] / T)      grid (ceil(H/16), B), 8 warps x 2 units
+//   se_gate_kernel:   gate[b, c] = sigmoid(sum_h W2[c, h] * hid[b, h])       grid (ceil(C/64), B), 8 warps x 8 units
+__global__ void __launch_bounds__(256)
+se_hidden_kernel(const float* __restrict__ pool, float inv_T, const float* __restrict__ w1, int C, int H,
+                 float* __restrict__ hid) {
+  extern __shared__ float sm[];   // mean[C]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = pool[(size_t)b * C + c] * inv_T;
   __syncthreads();
-  // hidden units: 4 rows of W1 per warp pass, 4 independent 128-byte loads per lane in flight
-  for (int h0 = warp * 4; h0 < H; h0 += nwarps * 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = lane; c < C; c += 32) {
-      const float mv = mean[c];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (h0 + u < H) a[u] = fmaf(__ldg(w1 + (size_t)(h0 + u) * C + c), mv, a[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float r = warp_sum(a[u]);
-      if (lane == 0 && h0 + u < H) hid[h0 + u] = fmaxf(r, 0.f);
-    }
+  const int h0 = blockIdx.x * 16 + warp * 2;
+  float a0 = 0.f, a1 = 0.f;
+  const bool ok0 = h0 < H, ok1 = h0 + 1 < H;
+  const float* r0 = w1 + (size_t)h0 * C;
+  const float* r1 = r0 + C;
+#pragma unroll 4
+  for (int c = lane; c < C; c += 32) {
+    const float mv = sm[c];
+    if (ok0) a0 = fmaf(__ldg(r0 + c), mv, a0);
+    if (ok1) a1 = fmaf(__ldg(r1 + c), mv, a1);
   }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (lane == 0) {
+    if (ok0) hid[(size_t)b * H + h0] = fmaxf(a0, 0.f);
+    if (ok1) hid[(size_t)b * H + h0 + 1] = fmaxf(a1, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const float* __restrict__ hid, const float* __restrict__ w2, int C, int H, float* __restrict__ gate) {
+  extern __shared__ float sm[];   // hid[H]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) sm[h] = hid[(size_t)b * H + h];
   __syncthreads();
-  // gates: 4 rows of W2 per warp pass
-  for (int c0 = warp * 4; c0 < C; c0 += nwarps * 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int h = lane; h < H; h += 32) {
-      const float hv = hid[h];
+  const int c0 = blockIdx.x * 64 + warp * 8;
+  float a[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < C) a[u] = fmaf(__ldg(w2 + (size_t)(c0 + u) * H + h), hv, a[u]);
-    }
+  for (int u = 0; u < 8; ++u) a[u] = 0.f;
+  for (int h = lane; h < H; h += 32) {
+    const float hv = sm[h];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float r = warp_sum(a[u]);
-      if (lane == 0 && c0 + u < C) gate[(size_t)b * C + c0 + u] = 1.f / (1.f + __expf(-r));
-    }
+    for (int u = 0; u < 8; ++u)
+      if (c0 + u < C) a[u] = fmaf(__ldg(w2 + (size_t)(c0 + u) * H + h), hv, a[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float r = warp_sum(a[u]);
+    if (lane == 0 && c0 + u < C) gate[(size_t)b * C + c0 + u] = 1.f / (1.f + __expf(-r));
   }
 }
 
@@ -269,14 +280,17 @@ extern "C" int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* s
   return TS_OK;
 }
 
-extern "C" int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* gate,
-                        void* stream) {
-  TS_REQUIRE(pool && w1 && w2 && gate, TS_ERR_INVALID, "ts_se_fc: null pointer");
-  TS_REQUIRE(B > 0 && C > 0 && H > 0 && T > 0, TS_ERR_INVALID, "ts_se_fc: bad sizes");
-  const size_t smem = (size_t)(C + H) * sizeof(float);
-  TS_REQUIRE(smem <= 48 * 1024, TS_ERR_UNSUPPORTED, "ts_se_fc: C=%d too large", C);
-  misc::se_fc_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, w2, C, H, gate);
-  TS_LAUNCH_CHECK("se_fc_kernel");
+extern "C" int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* hid,
+                        float* gate, void* stream) {
+  TS_REQUIRE(pool && w1 && w2 && hid && gate, TS_ERR_INVALID, "ts_se_fc: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && H > 0 && T > 0 && B <= 65535, TS_ERR_INVALID, "ts_se_fc: bad sizes");
+  TS_REQUIRE((size_t)C * sizeof(float) <= 48 * 1024 && (size_t)H * sizeof(float) <= 48 * 1024, TS_ERR_UNSUPPORTED,
+             "ts_se_fc: C=%d / H=%d too large", C, H);
+  dim3 g1(ceil_div(H, 16), B), g2(ceil_div(C, 64), B);
+  misc::se_hidden_kernel<<<g1, 256, C * sizeof(float), (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, C, H, hid);
+  TS_LAUNCH_CHECK("se_hidden_kernel");
+  misc::se_gate_kernel<<<g2, 256, H * sizeof(float), (cudaStream_t)stream>>>(hid, w2, C, H, gate);
+  TS_LAUNCH_CHECK("se_gate_kernel");
   return TS_OK;
 }
 

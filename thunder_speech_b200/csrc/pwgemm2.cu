@@ -120,22 +120,6 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
       const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
       const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
       const int m0 = mt * BM, t0 = nt * BN;
-      // pull the NEXT tile's activation boxes into L2 now (DRAM -> L2 overlaps this tile's main loop), so that its
-      // TMA loads see L2-hit latency and the 3-4 shared-memory stages suffice to keep the tensor pipe fed
-      {
-        const int ntile = tile + gridDim.x;
-        if (ntile < p.num_tiles) {
-          const int nrest = ntile / p.m_tiles;
-          const int nnt = nrest % p.n_tiles, nb = nrest / p.n_tiles;
-          for (int kc = 0; kc < num_k; ++kc) {
-            const bool seg1 = kc >= p.kc0;
-            const CUtensorMap* mb = seg1 ? &p.b1 : &p.b0;
-            const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j) ptx::tma_prefetch_3d(mb, nnt * BN + 64 * j, k0, nb);
-          }
-        }
-      }
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
         const int s = cnt % STAGES;
         ptx::mbar_wait(&empty_bar[s], ((cnt / STAGES) & 1) ^ 1);

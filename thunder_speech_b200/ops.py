@@ -224,8 +224,9 @@ def se_fc(pool: Tensor, T: int, w1: Tensor, w2: Tensor) -> Tensor:
     _need_cuda(pool, w1, w2)
     B, C = pool.shape
     gate = torch.empty_like(pool)
-    _lib.check(_lib.lib().ts_se_fc(_ptr(pool), B, C, w1.shape[0], T, _ptr(w1), _ptr(w2), _ptr(gate), _stream()),
-               "ts_se_fc")
+    hid = torch.empty((B, w1.shape[0]), device=pool.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ts_se_fc(_ptr(pool), B, C, w1.shape[0], T, _ptr(w1), _ptr(w2), _ptr(hid), _ptr(gate),
+                                   _stream()), "ts_se_fc")
     return gate
 
 
