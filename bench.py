@@ -41,6 +41,21 @@ WORKLOADS = {
 }
 
 
+#: bounded CPU sample (utterances per step) for the cpu_baseline / --impl reference legs: ~5-20 s of host work in total
+CPU_SAMPLE_BATCH = {"features": 64, "quartznet15x5": 16, "citrinet1024": 4}
+
+
+def traffic_per_launch(kernel: str, workload: str):
+    """DRAM bytes (read + write) per launch of `kernel`, from the committed ncu pass of one forward
+    (profiles/r01_dram_traffic.json, produced by tools/traffic_from_ncu.py); None if not measured."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)[workload][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def default_workload() -> str:
     try:
         from thunder_speech_b200 import runner  # noqa: F401
@@ -141,7 +156,7 @@ def run_reference(args):
     if rank != 0:
         return
     desc, B, secs, nfilt = WORKLOADS[args.workload]
-    sb = {"features": 8, "quartznet15x5": 2, "citrinet1024": 1}[args.workload]
+    sb = CPU_SAMPLE_BATCH[args.workload]
     rate, cores, sample, dt = cpu_port_rate(args.workload, min(args.steps, 5), min(args.warmup, 2), sb)
     out = {
         "impl": "reference", "metric": "audio-sec/sec", "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus,
@@ -236,6 +251,7 @@ def run_ours(args):
                 roof["peak"] = peaks["bf16_tflops_sustained"] * (1.0 if roof.get("unit") == "TFLOP/s" else 1.0)
             roof["frac"] = roof["achieved"] / roof["peak"]
             roof["peak_source"] = peak_src
+            roof["traffic"] = traffic_per_launch(roof["kernel"], args.workload)
         out = {
             "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -247,7 +263,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sb = {"features": 8, "quartznet15x5": 2, "citrinet1024": 1}[args.workload]
+                sb = CPU_SAMPLE_BATCH[args.workload]
                 rate, cores, sample, _ = cpu_port_rate(args.workload, 3, 1, sb)
                 out["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
             except Exception as e:  # the baseline is informative; never lose the GPU numbers over it
