@@ -66,6 +66,10 @@ def lib() -> ctypes.CDLL:
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # A/B switches for measurements, e.g. THUNDER_B200_OPTIONS="pw_pair=0,dw_tma=1"
+        for kv in filter(None, os.environ.get("THUNDER_B200_OPTIONS", "").split(",")):
+            k, v = kv.split("=")
+            check(handle.ts_set_option(k.strip().encode(), int(v)), "ts_set_option")
     return _lib
 
 

@@ -225,6 +225,11 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
                        int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                        int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
                        cudaStream_t st);
+int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
+                        int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
+                        int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                        cudaStream_t st);
+int option_pw_pair();
 }
 using namespace ts;
 
@@ -247,6 +252,13 @@ extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch
              "ts_pw_gemm: segment 1 pointers and cin1 disagree");
   TS_REQUIRE(B <= 65535, TS_ERR_UNSUPPORTED, "ts_pw_gemm: B > 65535");
 
+  // option pw_pair: 1 = CTA-pair kernel for K >= 1024, 2 = for every bf16-row GEMM with Cout > 128
+  if (out_dtype == TS_BF16 && option_pw_big() && option_pw_pair() > 0 &&
+      (option_pw_pair() >= 2 || cin0 + cin1 >= 1024)) {
+    const int rc = launch_pw_gemm_pair(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out,
+                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   if (out_dtype == TS_BF16 && option_pw_big()) {
     const int rc = launch_pw_gemm_big(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out,
                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream);

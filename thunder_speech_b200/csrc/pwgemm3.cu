@@ -1,0 +1,370 @@
+// 2-CTA (cta_group::2) variant of the persistent pointwise GEMM: a CLUSTER of two CTAs (two SMs of one TPC) computes a
+// 256(Cout) x 256(frames) tile per step with ONE tcgen05.mma.cta_group::2 stream issued by the leader CTA.
+//
+// Why: with cta_group::1 every M128 x N256 x K16 MMA re-reads 4 KB of A and 8 KB of B from its SM's shared memory per
+// 128 tensor cycles; measured on B200 (pwgemm2.cu with the TMA loads disabled) that caps the tensor pipe at ~58-64 %
+// busy.  In pair mode each SM holds its own 128 rows of A and only HALF of the B tile (the hardware reads the other
+// half from the peer's shared memory), so per-SM operand fill drops to 32 KB per k-chunk and the accumulator
+// (128 lanes x 256 columns per CTA) can be double buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+//   both CTAs   warp 0: TMA producer for its own A rows / B half, signalling the LEADER's full barrier
+//               warps 4-11: epilogue for its own 128 output channels (TMEM -> bf16 -> swizzled staging -> TMA store)
+//   leader CTA  warp 1: MMA issuer; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs
+#include "ts_common.cuh"
+#include "sm100_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace ts {
+namespace pw3 {
+
+constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;   // tile of the CTA PAIR
+constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 weight rows: 16 KB
+constexpr int B_BYTES = BK * (BN / 2) * 2;     // this CTA's half of the activation tile: 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGES = 5;
+constexpr int ACC = 2;
+constexpr int EPI_WARPS = 8;
+constexpr int STG_BYTES = 32 * 128;
+constexpr int THREADS = 384;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 + 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+struct Params {
+  CUtensorMap a0, b0, a1, b1, out;
+  int kc0, kc1;
+  int Cout, T, B;
+  int m_tiles, n_tiles, num_tiles;
+  const float* shift;
+  const int32_t* lens;
+  int out_pitch;
+  int relu;
+  float* pool;
+  const float* se_scale;
+  const __nv_bfloat16* y1;
+  int y1_pitch;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(ptx::smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          ptx::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(leader_bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          ptx::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(leader_bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma2_commit_mcast(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t* dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+pw_gemm_pair_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.kc0 + p.kc1;
+  const uint32_t rank = cluster_ctarank();     // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.a0);
+    ptx::prefetch_tensormap(&p.b0);
+    ptx::prefetch_tensormap(&p.out);
+    if (p.kc1 > 0) {
+      ptx::prefetch_tensormap(&p.a1);
+      ptx::prefetch_tensormap(&p.b1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 2);      // only the leader's copy is used: one arrival per CTA + both CTAs' bytes
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * EPI_WARPS * 32);   // leader's copy: epilogue threads of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / before the paired TMEM allocation
+  if (warp == 2) {
+    tmem2_alloc(tmem_slot, TMEM_COLS);
+    tmem2_relinquish();
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: runs ahead over this CTA's whole tile list =====
+    uint32_t cnt = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+      const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+      const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
+      const int m0 = mt * BM + 128 * (int)rank;          // this CTA's 128 output channels
+      const int t0 = nt * BN + (BN / 2) * (int)rank;     // this CTA's half of the frame tile
+      for (int kc = 0; kc < num_k; ++kc, ++cnt) {
+        const int s = cnt % STAGES;
+        ptx::mbar_wait(&empty_bar[s], ((cnt / STAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        if (rank == 0)
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+        else
+          mbar_arrive_remote(&full_bar[s], 0);
+        const bool seg1 = kc >= p.kc0;
+        const CUtensorMap* ma = seg1 ? &p.a1 : &p.a0;
+        const CUtensorMap* mb = seg1 ? &p.b1 : &p.b0;
+        const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
+        tma2_load_2d(sa, ma, &full_bar[s], k0, m0);                      // [128 rows x 64 k]
+#pragma unroll
+        for (int j = 0; j < BN / 128; ++j)
+          tma2_load_3d(sb + j * (BK * 128), mb, &full_bar[s], t0 + 64 * j, k0, b);
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, 0, 1);
+    uint32_t cnt = 0, it = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
+      const int a = it % ACC;
+      ptx::mbar_wait(&tmem_empty[a], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
+      ptx::tc_fence_after();
+      for (int kc = 0; kc < num_k; ++kc, ++cnt) {
+        const int s = cnt % STAGES;
+        ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t db = ptx::umma_desc(sb + k * 2048, BK * 128, 1024);
+          const uint64_t da = ptx::umma_desc(sa + k * 32, 0, 1024);
+          mma2_bf16_ss(tmem_base + a * BN, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+        }
+        mma2_commit_mcast(&empty_bar[s]);
+      }
+      mma2_commit_mcast(&tmem_full[a]);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int e = warp - 4;
+    const int q = warp & 3;          // TMEM lane quarter accessible to this warp
+    const int h = e >> 2;            // column half [128 h, 128 h + 128) of the 256-frame tile handled by this warp
+    uint8_t* stg = stg_base + e * STG_BYTES;
+    const uint32_t stg_row = ptx::smem_u32(stg) + lane * 128;
+    uint32_t it = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
+      const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+      const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
+      const int t0 = nt * BN + h * 128;
+      const int mrow0 = mt * BM + (int)rank * 128 + q * 32;
+      const int m = mrow0 + lane;
+      const bool m_ok = m < p.Cout;
+      const float shift = (m_ok && p.shift) ? p.shift[m] : 0.f;
+      const int len = p.lens ? min(p.lens[b], p.T) : p.T;
+      const float gate = (m_ok && p.se_scale) ? p.se_scale[(size_t)b * p.Cout + m] : 0.f;
+      float pooled = 0.f;
+      const int a = it % ACC;
+      ptx::mbar_wait(&tmem_full[a], (it / ACC) & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[64];
+        __syncwarp();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * 128 + cc * 64);
+        ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        ptx::tmem_ld_wait();
+        if (cc == 1) {  // this thread's part of the accumulator is read: tell the leader's MMA warp
+          ptx::tc_fence_before();
+          if (rank == 0)
+            ptx::mbar_arrive(&tmem_empty[a]);
+          else
+            mbar_arrive_remote(&tmem_empty[a], 0);
+        }
+        const int tb = t0 + cc * 64;
+        if (mrow0 < p.Cout && tb < p.out_pitch) {   // warp-uniform: something of this 32 x 64 block is stored
+          float r[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) r[j] = __uint_as_float(v[j]) + shift;
+          if (p.pool) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) pooled += (tb + j < p.T) ? r[j] : 0.f;
+          }
+          if (p.y1 && m_ok) {
+            const uint4* yp = reinterpret_cast<const uint4*>(p.y1 + ((size_t)b * p.Cout + m) * p.y1_pitch + tb);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint4 u = yp[g];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) {
+                r[g * 8 + 2 * hh] += gate * __uint_as_float(w[hh] << 16);
+                r[g * 8 + 2 * hh + 1] += gate * __uint_as_float(w[hh] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (lane == 0) bulk_wait_read0();   // previous TMA store has finished reading the staging tile
+          __syncwarp();
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) r[j] = fmaxf(r[j], 0.f);
+          }
+          if (tb + 64 > len) {   // block crosses the utterance end (warp-uniform): zero the tail
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (tb + j >= len) r[j] = 0.f;
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+              const int j = g * 8 + 2 * hh;
+              __nv_bfloat162 pr = __floats2bfloat162_rn(r[j], r[j + 1]);
+              pk[hh] = *reinterpret_cast<uint32_t*>(&pr);
+            }
+            // SWIZZLE_128B: 16-byte chunk g of row `lane` lives at chunk (g ^ (row & 7))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((g ^ (lane & 7)) << 4)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.out, stg, tb, mrow0, b);
+            bulk_commit();
+          }
+        }
+      }
+      if (p.pool && m_ok) atomicAdd(p.pool + (size_t)b * p.Cout + m, pooled);
+    }
+    if (lane == 0) bulk_wait0();   // all stores of this warp are complete before the CTA exits
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();   // the peer's shared memory / TMEM stay alive until both CTAs are done
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    tmem2_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace pw3
+
+// bf16-row outputs with Cout > 128 on CTA pairs; TS_ERR_UNSUPPORTED otherwise (caller falls back)
+int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
+                        int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
+                        int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                        cudaStream_t st) {
+  if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
+  pw3::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = tma::make_2d_bf16(&p.a0, w0, cin0, Cout, (uint64_t)cin0 * 2, pw3::BK, 128)) != TS_OK) return rc;
+  if ((rc = tma::make_3d_bf16(&p.b0, x0, T, cin0, B, (uint64_t)x0_pitch * 2, (uint64_t)cin0 * x0_pitch * 2, 64, pw3::BK,
+                              1)) != TS_OK)
+    return rc;
+  p.kc0 = ceil_div(cin0, pw3::BK);
+  if (cin1 > 0) {
+    if ((rc = tma::make_2d_bf16(&p.a1, w1, cin1, Cout, (uint64_t)cin1 * 2, pw3::BK, 128)) != TS_OK) return rc;
+    if ((rc = tma::make_3d_bf16(&p.b1, x1, T, cin1, B, (uint64_t)x1_pitch * 2, (uint64_t)cin1 * x1_pitch * 2, 64,
+                                pw3::BK, 1)) != TS_OK)
+      return rc;
+    p.kc1 = ceil_div(cin1, pw3::BK);
+  }
+  if ((rc = tma::make_3d_bf16(&p.out, out, out_pitch, Cout, B, (uint64_t)out_pitch * 2, (uint64_t)Cout * out_pitch * 2,
+                              64, 32, 1)) != TS_OK)
+    return rc;
+  p.Cout = Cout; p.T = T; p.B = B;
+  p.m_tiles = ceil_div(Cout, pw3::BM);
+  p.n_tiles = ceil_div(out_pitch, pw3::BN);
+  p.num_tiles = p.m_tiles * p.n_tiles * B;
+  p.shift = shift; p.lens = lens; p.out_pitch = out_pitch; p.relu = relu;
+  p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    TS_CUDA(cudaGetDevice(&dev));
+    TS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    TS_CUDA(cudaFuncSetAttribute(pw3::pw_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pw3::SMEM_BYTES));
+  }
+  int pairs = num_sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  pw3::pw_gemm_pair_kernel<<<2 * pairs, pw3::THREADS, pw3::SMEM_BYTES, st>>>(p);
+  TS_LAUNCH_CHECK("pw_gemm_pair_kernel");
+  return TS_OK;
+}
+
+}  // namespace ts
