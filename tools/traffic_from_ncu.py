@@ -5,7 +5,7 @@ import csv, json, os, sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASS = {"pw_gemm": "pw_gemm_big_kernel", "dw_tma": "dw_tma_kernel", "dw_mma": "dw_tma_kernel", "dw_fast": "dw_tma_kernel",
+CLASS = {"pw_gemm": "pw_gemm_pair_kernel", "dw_tma": "dw_tma_kernel", "dw_mma": "dw_tma_kernel", "dw_fast": "dw_tma_kernel",
          "logmel": "logmel_kernel"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
