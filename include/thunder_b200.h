@@ -44,6 +44,7 @@ int64_t ts_launch_count(void);
 /* runtime switches for A/B measurements: "dw_mma" (default 1) = stride-1 depthwise convs on the tensor cores,
  * "pw_big" (default 1) = persistent 256x256-tile GEMM for bf16 outputs with Cout > 128, "pw_pair" (default 2) = run it
  * on CTA pairs (tcgen05 cta_group::2; 1 = only for K >= 1024, 0 = single-CTA kernel),
+ * "pdl" (default 0) = programmatic dependent launch for the two hot kernels (measured: no gain),
  * "dw_tma" (default 1) = TMA-fed Toeplitz kernel for pre-masked inputs, "dw_base_offset" (descriptor experiment) */
 int ts_set_option(const char* name, int value);
 /* pitch (in frames) of a padded activation row holding T frames */

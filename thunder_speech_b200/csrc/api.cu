@@ -21,6 +21,8 @@ static std::atomic<int> g_opt_dw_mma{1};
 static std::atomic<int> g_opt_pw_big{1};
 static std::atomic<int> g_opt_dw_tma{1};
 static std::atomic<int> g_opt_pw_bn{0};
+static std::atomic<int> g_opt_pdl{0};
+int option_pdl() { return g_opt_pdl.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_pw_pair{2};
 int option_pw_pair() { return g_opt_pw_pair.load(std::memory_order_relaxed); }
 int option_pw_bn() { return g_opt_pw_bn.load(std::memory_order_relaxed); }
@@ -40,6 +42,10 @@ extern "C" int ts_row_pitch(int T) { return T <= 0 ? 0 : ts::round_up(T, ts::kRo
 extern "C" int ts_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "dw_mma") == 0) {
     ts::g_opt_dw_mma.store(value);
+    return TS_OK;
+  }
+  if (name != nullptr && strcmp(name, "pdl") == 0) {
+    ts::g_opt_pdl.store(value);
     return TS_OK;
   }
   if (name != nullptr && strcmp(name, "pw_pair") == 0) {

@@ -123,9 +123,11 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();   // the next kernel may begin its prologue once every CTA of this grid is here
   if (warp == 0) {
     // ===== TMA producer (starts streaming immediately; the Toeplitz build overlaps) =====
     if (lane == 0) {
+      pdl_wait();              // first read of the previous kernel's output
       for (int n = 0; n < ntiles; ++n) {
         const int s = n % NSTAGE;
         ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1);
@@ -199,6 +201,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     const int bl = row / p.R, i = row - bl * p.R;
     const int t = 64 * i;
     const uint32_t srow = ptx::smem_u32(sO) + row * 128;
+    pdl_wait();                // no global write of this grid may overtake the previous grid's reads
     for (int n = 0; n < ntiles; ++n) {
       const int a = n % ACC_STAGES;
       const int b0 = (tile0 + n) * p.NB;
@@ -308,9 +311,9 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
   }
   dim3 grid(C, groups);
   if (p.NQ <= 3)
-    dwt2::dw_tma_kernel<3><<<grid, dwt2::THREADS, dwt2::smem_bytes(p.NQ), st>>>(p);
+    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<3>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ), st, option_pdl() != 0, p));
   else
-    dwt2::dw_tma_kernel<5><<<grid, dwt2::THREADS, dwt2::smem_bytes(p.NQ), st>>>(p);
+    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<5>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ), st, option_pdl() != 0, p));
   TS_LAUNCH_CHECK("dw_tma_kernel");
   return TS_OK;
 }

@@ -165,6 +165,10 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; from here on we
+  // read its output.  Let the next kernel start its own prologue as soon as all our CTAs got this far.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: runs ahead over this CTA's whole tile list =====
@@ -362,7 +366,8 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   }
   int pairs = num_sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  pw3::pw_gemm_pair_kernel<<<2 * pairs, pw3::THREADS, pw3::SMEM_BYTES, st>>>(p);
+  TS_CUDA(launch_pdl(pw3::pw_gemm_pair_kernel, dim3(2 * pairs), dim3(pw3::THREADS), pw3::SMEM_BYTES, st,
+                     option_pdl() != 0, p));
   TS_LAUNCH_CHECK("pw_gemm_pair_kernel");
   return TS_OK;
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <utility>
 
 #include "../../include/thunder_b200.h"
 
@@ -51,6 +52,33 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 constexpr int kRowPitchAlign = 64;  // frames; 128 bytes of bf16
+
+int option_pdl();  // 1: hot kernels are launched with programmatic stream serialization (PDL)
+
+// ---- programmatic dependent launch --------------------------------------------------------------
+// Device side: `pdl_launch_dependents()` lets the NEXT kernel in the stream start its prologue as soon as every CTA of
+// this grid has executed it; `pdl_wait()` blocks until the PREVIOUS grid has completed and its writes are visible.
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Host side: launch with the programmatic-stream-serialization attribute (captured into CUDA graphs as a
+// programmatic dependency edge).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
