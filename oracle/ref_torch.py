@@ -44,13 +44,16 @@ def _mask(x, lengths):
     return x.masked_fill(~m.unsqueeze(1), 0)
 
 
-def _bn(st, p, x):
+def _bn(st, p, x, train=False):
+    """eval: running statistics.  train: batch statistics over ALL (batch, time) positions incl. padded frames, and the
+    running statistics in `st` are updated in place with momentum 0.1 (nn.BatchNorm1d(eps=1e-3, momentum=0.1))."""
     return F.batch_norm(x, st[p + ".running_mean"], st[p + ".running_var"], st[p + ".weight"], st[p + ".bias"],
-                        False, 0.1, 1e-3)
+                        train, 0.1, 1e-3)
 
 
-def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str):
-    """quartznet/blocks.py:317-338 / citrinet/blocks.py:177-197 (eval)."""
+def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str, train: bool = False):
+    """quartznet/blocks.py:317-338 / citrinet/blocks.py:177-197; differentiable (torch autograd) when the tensors in
+    `st` require grad -- the oracle of the training step (module.py:102-127)."""
     out, out_len = x, lengths
     strides = cfg.sub_strides()
     for r in range(cfg.repeat):
@@ -63,11 +66,11 @@ def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str)
                            groups=out.shape[1])
             out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
             out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i + 1}.conv.weight"])
-            out = _bn(st, f"{prefix}mconv.{i + 2}.layer.0", out)
+            out = _bn(st, f"{prefix}mconv.{i + 2}.layer.0", out, train)
         else:
             out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i}.conv.weight"], None, s, pad, cfg.dilation)
             out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
-            out = _bn(st, f"{prefix}mconv.{i + 1}.layer.0", out)
+            out = _bn(st, f"{prefix}mconv.{i + 1}.layer.0", out, train)
         if r != cfg.repeat - 1:
             out = F.relu(out)
     if cfg.kind == "citrinet":
@@ -77,14 +80,22 @@ def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str)
         out = out * torch.sigmoid(y).unsqueeze(-1)
     if cfg.residual:
         res = F.conv1d(_mask(x, lengths), st[f"{prefix}res.0.conv.weight"], None, cfg.residual_stride())
-        out = out + _bn(st, f"{prefix}res.1.layer.0", res)
+        out = out + _bn(st, f"{prefix}res.1.layer.0", res, train)
     return F.relu(out), out_len
 
 
-def encoder(x, lengths, cfgs: List[R.BlockCfg], st):
+def encoder(x, lengths, cfgs: List[R.BlockCfg], st, train: bool = False):
     for bi, cfg in enumerate(cfgs):
-        x, lengths = block(x, lengths, cfg, st, f"{bi}.")
+        x, lengths = block(x, lengths, cfg, st, f"{bi}.", train)
     return x, lengths
+
+
+def ctc_loss(logits: torch.Tensor, y: torch.Tensor, prob_lengths: torch.Tensor, y_lengths: torch.Tensor,
+             blank_idx: int) -> torch.Tensor:
+    """calculate_ctc (src/thunder/ctc_loss.py:15-47): permute -> log_softmax -> F.ctc_loss(mean, zero_infinity)."""
+    logprobs = F.log_softmax(logits.permute(2, 0, 1), dim=2)
+    return F.ctc_loss(logprobs, y, prob_lengths.long(), y_lengths, blank=blank_idx, reduction="mean",
+                      zero_infinity=True)
 
 
 def predict_ids(audio: torch.Tensor, cfgs, st, dec_w, dec_b, nfilt: int):
@@ -104,12 +115,16 @@ def make_workload(name: str, batch: int, samples: int, nfilt: int):
     """Closure running one step of a bench workload on CPU + a description of the bounded sample."""
     from thunder_speech_b200 import synth
 
-    torch.set_grad_enabled(False)
     x = torch.from_numpy(synth.audio(batch, samples, 1234, "noise"))
     lens = torch.full((batch,), samples, dtype=torch.long)
     if name == "features":
         fb = torch.from_numpy(R.mel_filterbank(257, nfilt, 16000))
-        return (lambda: features(x, lens, nfilt=nfilt, fb=fb)), f"B={batch} x {samples / 16000:.0f} s, torch CPU fp32"
+
+        def feat_step():
+            with torch.no_grad():
+                return features(x, lens, nfilt=nfilt, fb=fb)
+
+        return feat_step, f"B={batch} x {samples / 16000:.0f} s, torch CPU fp32"
     if name == "quartznet15x5":
         cfgs = R.quartznet_cfgs(repeat_blocks=3)
         st = to_torch(synth.encoder_state(synth.quartznet_block_list(repeat_blocks=3), seed=0))
@@ -126,7 +141,8 @@ def make_workload(name: str, batch: int, samples: int, nfilt: int):
         raise ValueError(name)
 
     def step():
-        ids, _, _ = predict_ids(x, cfgs, st, dec["weight"], dec["bias"], nfilt)
+        with torch.no_grad():
+            ids, _, _ = predict_ids(x, cfgs, st, dec["weight"], dec["bias"], nfilt)
         return R.decode_prediction(ids.numpy(), vocab)
 
     return step, f"B={batch} x {samples / 16000:.0f} s predict() incl. greedy decode, torch CPU fp32"
