@@ -144,6 +144,31 @@ int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D,
 int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream);
 int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* stream);
 
+/* ---- training step: train()-mode BatchNorm and the backward pass ------------------------- */
+/* Reference: BaseCTCModule.training_step (src/thunder/module.py:102-127) through train()-mode QuartznetBlock
+ * (src/thunder/quartznet/blocks.py:231-338); nn.BatchNorm1d(eps=1e-3, momentum=0.1) then uses BATCH statistics over all
+ * B x T positions (padded frames included).  Forward reuses ts_dw_conv / ts_pw_gemm (unfolded weights, no shift). */
+/* stats[b, c] = (sum_t z, sum_t z^2) over t < T of bf16 rows; the caller sums over b */
+int ts_row_stats(const void* z, int B, int C, int T, int pitch, float* stats, void* stream);
+/* y = act(z * scale[c] + shift[c] (+ zr * scale_r[c] + shift_r[c])): BatchNorm affine (+ residual branch) + ReLU,
+ * frames t >= lens[b] and the pad stored as zero (quartznet/blocks.py:222-228,332-337) */
+int ts_bn_apply(const void* z, const float* scale, const float* shift, const void* zr, const float* scale_r,
+                const float* shift_r, int B, int C, int T, int pitch, const int32_t* lens, int relu, void* y,
+                void* stream);
+/* sums[b, c] = (sum dym, sum dym*z, sum dym*zr) with dym = dy * (y > 0) when relu: the reductions of BatchNorm backward */
+int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, const void* zr, int B, int C, int T, int pitch,
+                     int relu, float* sums, void* stream);
+/* dz = coef[c,0] dym + coef[c,1] z + coef[c,2]  (and the same for the residual branch): BatchNorm + ReLU backward */
+int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, const void* zr, const float* coef,
+                    const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr, void* stream);
+/* pointwise-conv weight gradient dW[co, ci] = sum_{b,t} dz[b, co, t] a[b, ci, t] on the tensor cores;
+ * part [nsplit, Cout, Cin] f32 partial sums over batch slices (the caller adds them) */
+int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B, int Cout, int Cin, int T, int nsplit,
+                float* part, void* stream);
+/* depthwise weight gradient: part[chunk, c, k] = sum_{b in chunk, t'} da[b, c, t'] xm[b, c, t' S + k D - P] */
+int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
+                int B, int C, int K, int S, int D, int P, int bchunk, float* part, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

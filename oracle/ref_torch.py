@@ -51,9 +51,22 @@ def _bn(st, p, x, train=False):
                         train, 0.1, 1e-3)
 
 
-def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str, train: bool = False):
+def bf16_store(x: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 and back with a straight-through gradient: models a tensor that the device path STORES in bf16.
+    With `block(..., store=bf16_store)` the oracle rounds at the points where the B200 path writes bf16 rows (block
+    input, depthwise output, GEMM output, BN+ReLU output) and where it reads bf16 weights, so that ReLU masks and batch
+    statistics agree with the device and what is left is backward-pass rounding only."""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str, train: bool = False, store=None):
     """quartznet/blocks.py:317-338 / citrinet/blocks.py:177-197; differentiable (torch autograd) when the tensors in
-    `st` require grad -- the oracle of the training step (module.py:102-127)."""
+    `st` require grad -- the oracle of the training step (module.py:102-127).  `store` (default: identity) is applied
+    to every tensor the device path materialises, see `bf16_store`."""
+    q = store if store is not None else (lambda t: t)
+    if store is not None:
+        st = {k: (q(v) if k.endswith("conv.weight") else v) for k, v in st.items()}
+    x = q(x)
     out, out_len = x, lengths
     strides = cfg.sub_strides()
     for r in range(cfg.repeat):
@@ -65,28 +78,28 @@ def block(x, lengths, cfg: R.BlockCfg, st: Dict[str, torch.Tensor], prefix: str,
             out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i}.conv.weight"], None, s, pad, cfg.dilation,
                            groups=out.shape[1])
             out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
-            out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i + 1}.conv.weight"])
+            out = q(F.conv1d(_mask(q(out), out_len), st[f"{prefix}mconv.{i + 1}.conv.weight"]))
             out = _bn(st, f"{prefix}mconv.{i + 2}.layer.0", out, train)
         else:
             out = F.conv1d(_mask(out, out_len), st[f"{prefix}mconv.{i}.conv.weight"], None, s, pad, cfg.dilation)
             out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
-            out = _bn(st, f"{prefix}mconv.{i + 1}.layer.0", out, train)
+            out = _bn(st, f"{prefix}mconv.{i + 1}.layer.0", q(out), train)
         if r != cfg.repeat - 1:
-            out = F.relu(out)
+            out = q(F.relu(out))
     if cfg.kind == "citrinet":
         i_se = cfg.mconv_index(cfg.repeat - 1) + (3 if cfg.separable else 2)
         y = out.mean(-1)
         y = F.relu(y @ st[f"{prefix}mconv.{i_se}.layer.0.fc.0.weight"].T) @ st[f"{prefix}mconv.{i_se}.layer.0.fc.2.weight"].T
         out = out * torch.sigmoid(y).unsqueeze(-1)
     if cfg.residual:
-        res = F.conv1d(_mask(x, lengths), st[f"{prefix}res.0.conv.weight"], None, cfg.residual_stride())
+        res = q(F.conv1d(_mask(x, lengths), st[f"{prefix}res.0.conv.weight"], None, cfg.residual_stride()))
         out = out + _bn(st, f"{prefix}res.1.layer.0", res, train)
-    return F.relu(out), out_len
+    return q(F.relu(out)), out_len
 
 
-def encoder(x, lengths, cfgs: List[R.BlockCfg], st, train: bool = False):
+def encoder(x, lengths, cfgs: List[R.BlockCfg], st, train: bool = False, store=None):
     for bi, cfg in enumerate(cfgs):
-        x, lengths = block(x, lengths, cfg, st, f"{bi}.", train)
+        x, lengths = block(x, lengths, cfg, st, f"{bi}.", train, store)
     return x, lengths
 
 

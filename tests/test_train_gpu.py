@@ -1,0 +1,267 @@
+"""GPU parity of the training step (train()-mode forward, backward, parameter gradients, BatchNorm running statistics)
+against goldens produced by the reference's own modules with torch autograd (tests/golden/train.npz) and against the
+autograd-capable torch port.  bf16 activations / gradients: tolerances are relative L2 errors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_numpy as R
+from oracle.make_golden_train import TRAIN_BLOCK_CASES, block_case, tiny_model_case
+from thunder_speech_b200 import ops, synth
+from thunder_speech_b200.blocks import conv1d_decoder
+from thunder_speech_b200.module import CTCModule
+from thunder_speech_b200.quartznet.blocks import QuartznetBlock, QuartznetEncoder
+from thunder_speech_b200.quartznet.transform import FilterbankFeatures
+from thunder_speech_b200.text_processing import BatchTextTransformer
+from thunder_speech_b200.train import BlockTrainer, CTCTrainStep
+
+pytestmark = pytest.mark.gpu
+
+# Gradients are compared by relative L2 error.  With bf16 activations the ReLU masks of ~0.3 % of the elements (those with
+# |y| below one bf16 ulp of the pre-activation) flip relative to the fp32 reference; each flip changes dy*mask by a whole
+# element, so the gradient error is ~sqrt(fraction flipped) ~ 5 % on these 100-150 sample batches (the single
+# sub-block cases agree to 0.3-2 %).
+GRAD_TOL = 8e-2
+
+
+@pytest.fixture(scope="module")
+def gtrain():
+    return np.load("tests/golden/train.npz", allow_pickle=False)
+
+
+def l2(a, b):
+    return rel_err(a, b)[1]
+
+
+@pytest.mark.parametrize("ci", range(len(TRAIN_BLOCK_CASES)))
+def test_block_training_step_vs_reference(gtrain, ci):
+    name, cfg, st, x, lens, Rm = block_case(ci)
+    blk = QuartznetBlock(cfg["in_channels"], cfg["out_channels"], repeat=cfg["repeat"], kernel_size=(cfg["kernel_size"],),
+                         stride=(cfg["stride"],), dilation=(cfg["dilation"],), residual=cfg["residual"],
+                         separable=cfg["separable"])
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    blk = blk.cuda().train()
+    bt = BlockTrainer(blk)
+    l32 = torch.from_numpy(lens.astype(np.int32)).cuda()
+    rows = ops.pack_rows(torch.from_numpy(x).cuda(), l32)
+    y, T_out, lo, tape = bt.forward(rows, x.shape[-1], l32, zero_tail=False)
+    out = ops.unpack_rows(y, T_out).cpu().numpy()
+    assert out.shape == gtrain[f"{name}.out"].shape
+    assert np.array_equal(lo.cpu().numpy(), gtrain[f"{name}.out_lengths"])
+    assert l2(out, gtrain[f"{name}.out"]) < 2e-2
+    need_dx = cfg["stride"] == 1
+    dx = bt.backward(tape, ops.pack_rows(torch.from_numpy(Rm).cuda()), need_dx=need_dx)
+    torch.cuda.synchronize()
+    if need_dx:
+        e = l2(ops.unpack_rows(dx, x.shape[-1]).cpu().numpy(), gtrain[f"{name}.dx"])
+        assert e < GRAD_TOL, (name, "dx", e)
+    for k, p in blk.named_parameters():
+        ref = gtrain[f"{name}.grad.{k}"]
+        e = l2(p.grad.cpu().numpy(), ref)
+        assert e < GRAD_TOL, (name, k, e)
+    for k, b in blk.named_buffers():
+        if "running" in k:
+            assert rel_err(b.cpu().numpy(), gtrain[f"{name}.buf.{k}"])[0] < 1e-2, (name, k)
+
+
+def test_pw_wgrad_and_dw_wgrad_ops():
+    from thunder_speech_b200.train import dw_wgrad, pw_wgrad
+
+    rng = np.random.default_rng(3)
+    B, Cout, Cin, T = 5, 300, 140, 333
+    dz = rng.standard_normal((B, Cout, T)).astype(np.float32)
+    a = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    dzr, ar = ops.pack_rows(torch.from_numpy(dz).cuda()), ops.pack_rows(torch.from_numpy(a).cuda())
+    got = pw_wgrad(dzr, ar, T).cpu().numpy()
+    ref = np.einsum("bot,bit->oi", dzr.float().cpu().numpy()[:, :, :T].astype(np.float64),
+                    ar.float().cpu().numpy()[:, :, :T].astype(np.float64))
+    assert rel_err(got, ref)[0] < 1e-4
+    for (K, S, D) in ((5, 1, 1), (33, 2, 1), (9, 1, 2)):
+        P = R.get_same_padding(K, S, D)
+        Tin = 201
+        Tout = (Tin + 2 * P - D * (K - 1) - 1) // S + 1
+        C = 7
+        x = rng.standard_normal((B, C, Tin)).astype(np.float32)
+        da = rng.standard_normal((B, C, Tout)).astype(np.float32)
+        lens = np.array([201, 150, 100, 201, 7], np.int32)
+        xr, dar = ops.pack_rows(torch.from_numpy(x).cuda()), ops.pack_rows(torch.from_numpy(da).cuda())
+        got = dw_wgrad(dar, Tout, xr, Tin, torch.from_numpy(lens).cuda(), K, S, D, P).cpu().numpy()
+        xm = np.where(np.arange(Tin)[None, None, :] < lens[:, None, None], xr.float().cpu().numpy()[:, :, :Tin], 0).astype(np.float64)
+        xp = np.pad(xm, ((0, 0), (0, 0), (P, P + S)))
+        dd = dar.float().cpu().numpy()[:, :, :Tout].astype(np.float64)
+        ref = np.stack([(dd * xp[:, :, k * D: k * D + (Tout - 1) * S + 1: S]).sum((0, 2)) for k in range(K)], axis=1)
+        assert rel_err(got, ref)[0] < 1e-4, (K, S, D)
+
+
+def test_model_training_step_vs_reference(gtrain):
+    filters, kernels, st, dec, x, lens, y, y_len = tiny_model_case()
+    enc = QuartznetEncoder(filters=filters, kernel_sizes=kernels, repeat_blocks=1)
+    enc.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    d = conv1d_decoder(1024, 29)
+    d.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()})
+    m = CTCModule(enc, d, FilterbankFeatures(nfilt=64, dither=0.0), BatchTextTransformer(synth.quartznet_vocab())).cuda()
+    m.encoder.train(); m.decoder.train()
+    step = CTCTrainStep(m, lr=1e-3)
+    loss = step.loss_and_grads(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(y).cuda(),
+                               torch.from_numpy(y_len).cuda())
+    ref_loss = float(gtrain["model.loss"])
+    assert abs(loss.item() - ref_loss) < 3e-2 * abs(ref_loss), (loss.item(), ref_loss)
+    # the tiny golden case (62 BatchNorm samples per channel) is too ill-conditioned to compare deep gradients in bf16;
+    # gradient direction is checked below against the oracle on a larger batch
+    # an optimiser step runs and changes the parameters
+    w0 = m.decoder.weight.detach().clone()
+    step.opt.step()
+    assert not torch.equal(w0, m.decoder.weight)
+
+
+def _model_case():
+    filters, kernels = [32, 32, 32, 32, 32], [5, 7, 9, 11, 13]
+    st = synth.encoder_state(synth.quartznet_block_list(filters=filters, kernel_sizes=kernels, repeat_blocks=1), seed=31)
+    dec = synth.decoder_state(1024, 29, seed=32)
+    x = synth.audio(8, 32000, 33, "tones")
+    lens = np.array([32000, 32000, 30000, 28000, 25000, 22222, 20000, 16000], np.int64)
+    rng = np.random.default_rng(34)
+    y = rng.integers(0, 28, (8, 12)).astype(np.int64)
+    y_len = rng.integers(4, 13, 8).astype(np.int64)
+    return filters, kernels, st, dec, x, lens, y, y_len
+
+
+def _oracle_model(case, store=None, steps=0, lr=1e-3):
+    """Autograd torch port of the training step on CPU (fp32, or fp32 with bf16 STORAGE simulated at the points where
+    the device path writes bf16 rows).  Returns (losses, grads of the first step)."""
+    from oracle import ref_torch as RT
+
+    filters, kernels, st, dec, x, lens, y, y_len = case
+    cfgs = R.quartznet_cfgs(filters=filters, kernel_sizes=kernels, repeat_blocks=1)
+    stt = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st.items()}
+    for k, v in stt.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    dw_, db_ = torch.from_numpy(dec["weight"]).clone().requires_grad_(True), torch.from_numpy(dec["bias"]).clone().requires_grad_(True)
+    params = [v for v in stt.values() if v.requires_grad] + [dw_, db_]
+    opt = torch.optim.AdamW(params, lr=lr)
+    with torch.no_grad():
+        f, fl = RT.features(torch.from_numpy(x), torch.from_numpy(lens))
+    losses, grads = [], None
+    for it in range(max(steps, 1)):
+        opt.zero_grad()
+        e, el = RT.encoder(f, fl, cfgs, stt, train=True, store=store)
+        loss = RT.ctc_loss(torch.nn.functional.conv1d(e, dw_, db_), torch.from_numpy(y), el, torch.from_numpy(y_len), 28)
+        loss.backward()
+        losses.append(loss.item())
+        if grads is None:
+            grads = {k: v.grad.numpy().copy() for k, v in stt.items() if v.requires_grad}
+            grads["decoder.weight"], grads["decoder.bias"] = dw_.grad.numpy().copy(), db_.grad.numpy().copy()
+        if steps:
+            opt.step()
+    return losses, grads
+
+
+def _device_model(case, lr=1e-3):
+    filters, kernels, st, dec, x, lens, y, y_len = case
+    enc = QuartznetEncoder(filters=filters, kernel_sizes=kernels, repeat_blocks=1)
+    enc.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    d = conv1d_decoder(1024, 29)
+    d.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()})
+    m = CTCModule(enc, d, FilterbankFeatures(nfilt=64, dither=0.0), BatchTextTransformer(synth.quartznet_vocab())).cuda()
+    m.encoder.train(); m.decoder.train()
+    batch = (torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(y_len).cuda())
+    return m, CTCTrainStep(m, lr=lr), batch
+
+
+def _cos(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
+
+
+def test_model_gradients_vs_oracle_larger_batch():
+    """Per-parameter gradients of the full training step (8 utterances x 2 s, 28 conv+BN+ReLU layers) against the autograd
+    torch port.  BatchNorm + ReLU at random init is in the chaotic regime (a perturbation grows ~1.15x per layer: the fp32
+    port and the SAME port with bf16 storage already differ by 17 % at the encoder output), so the criterion for the deep
+    layers is relative: the device gradients must be as close to the fp32 oracle as the bf16-storage oracle is.  Kernel
+    correctness proper is pinned by the block-level tests above (<= 2 % against the bf16-storage oracle)."""
+    from oracle import ref_torch as RT
+
+    case = _model_case()
+    (ref_loss,), ref = _oracle_model(case)
+    (sim_loss,), sim = _oracle_model(case, store=RT.bf16_store)
+    m, step, batch = _device_model(case)
+    loss = step.loss_and_grads(*batch)
+    assert abs(loss.item() - ref_loss) < 2e-2 * abs(ref_loss), (loss.item(), ref_loss)
+    got = {k: p.grad.float().cpu().numpy() for k, p in m.encoder.named_parameters()}
+    got["decoder.weight"], got["decoder.bias"] = m.decoder.weight.grad.cpu().numpy(), m.decoder.bias.grad.cpu().numpy()
+    for k in ref:
+        na, nb = np.linalg.norm(got[k]), np.linalg.norm(ref[k])
+        assert abs(na - nb) < 0.4 * nb + 1e-8, (k, na, nb)
+    # per encoder block (all its parameters concatenated -- single 32-element BN vectors are too noisy to compare)
+    groups = sorted({k.split(".")[0] for k in ref})
+    cat = lambda g, grp: np.concatenate([g[k].ravel() for k in sorted(ref) if k.split(".")[0] == grp])
+    ours = {grp: _cos(cat(got, grp), cat(ref, grp)) for grp in groups}
+    base = {grp: _cos(cat(sim, grp), cat(ref, grp)) for grp in groups}
+    print("cosine vs fp32 oracle per block: device", {k: round(v, 3) for k, v in ours.items()})
+    print("                   bf16-storage oracle", {k: round(v, 3) for k, v in base.items()})
+    for grp in groups:
+        assert ours[grp] > base[grp] - 0.1, (grp, ours[grp], base[grp])
+    assert np.mean(list(ours.values())) > np.mean(list(base.values())) - 0.03
+    # shallow end of the backward pass: few layers of amplification, absolute bounds hold
+    assert ours["decoder"] > 0.995 and ours["7"] > 0.97 and ours["6"] > 0.92
+
+
+def test_model_loss_trajectory_vs_oracle():
+    """Six AdamW steps on one batch: the loss curve of the device training step follows the fp32 oracle's (within 10 %
+    during the steep descent: 24.8 -> 13.3 -> 6.4 -> 4.8 -> 5.0 measured vs 24.8 -> 13.9 -> 6.3 -> 5.1 -> 5.0)."""
+    case = _model_case()
+    ref_losses, _ = _oracle_model(case, steps=6, lr=2e-3)
+    m, step, batch = _device_model(case, lr=2e-3)
+    losses = [step.step(*batch).item() for _ in range(6)]
+    print("losses device", losses, "oracle", ref_losses)
+    assert ref_losses[-1] < 0.9 * ref_losses[0]
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 1e-1 * abs(b), (losses, ref_losses)
+
+
+SIM_BLOCK_CASES = [  # cin, cout, K, repeat, B, T, residual
+    (32, 32, 5, 1, 8, 101, False),
+    (32, 32, 13, 5, 8, 101, True),
+    (256, 32, 5, 5, 8, 101, True),
+    (64, 128, 11, 3, 4, 300, True),
+]
+
+
+@pytest.mark.parametrize("cin,cout,K,rep,B,T,res", SIM_BLOCK_CASES)
+def test_block_gradients_vs_bf16_storage_oracle(cin, cout, K, rep, B, T, res):
+    """Forward and every gradient of one block against the autograd port with bf16 storage simulated (same ReLU masks and
+    batch statistics as the device): what is left is backward-pass bf16 rounding."""
+    from oracle import ref_torch as RT
+
+    rng = np.random.Generator(np.random.PCG64(cin + K))
+    st = synth.block_state(rng, "", cin, cout, rep, K, res, True)
+    x = np.maximum(rng.standard_normal((B, cin, T)), 0).astype(np.float32)
+    lens = np.sort(rng.integers(T // 2, T + 1, B))[::-1].astype(np.int64).copy()
+    lens[0] = T
+    m = (np.arange(T)[None, :] < lens[:, None])[:, None, :]
+    Rm = np.where(m, rng.standard_normal((B, cout, T)), 0).astype(np.float32)
+    cfg = R.BlockCfg(cin, cout, repeat=rep, kernel_size=K, residual=res, separable=True)
+    stt = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st.items()}
+    for k, v in stt.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    xt = torch.from_numpy(np.where(m, x, 0).astype(np.float32)).requires_grad_(True)
+    y, _ = RT.block(xt, torch.from_numpy(lens), cfg, stt, "", train=True, store=RT.bf16_store)
+    (y * torch.from_numpy(Rm)).sum().backward()
+    blk = QuartznetBlock(cin, cout, repeat=rep, kernel_size=(K,), residual=res, separable=True)
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    blk = blk.cuda().train()
+    bt = BlockTrainer(blk)
+    l32 = torch.from_numpy(lens.astype(np.int32)).cuda()
+    yy, T_out, lo, tape = bt.forward(ops.pack_rows(torch.from_numpy(x).cuda(), l32), T, l32, zero_tail=True)
+    assert l2(ops.unpack_rows(yy, T_out).cpu().numpy(), np.where(m, y.detach().numpy(), 0)) < 5e-3
+    dx = bt.backward(tape, ops.pack_rows(torch.from_numpy(Rm).cuda()), need_dx=True)
+    # single-ulp bf16 differences in the forward cascade through the five sub-blocks (a handful of ReLU masks end up
+    # differing by the last one): 0.3-0.5 % for 1-3 sub-blocks, 0.6-3 % for 5
+    tol = 2e-2 if rep <= 3 else 5e-2
+    assert l2(ops.unpack_rows(dx, T).cpu().numpy(), xt.grad.numpy()) < tol
+    for k, p in blk.named_parameters():
+        e = l2(p.grad.cpu().numpy(), stt[k].grad.numpy())
+        assert e < tol, (k, e)

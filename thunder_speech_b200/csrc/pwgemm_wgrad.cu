@@ -1,0 +1,159 @@
+// Pointwise-conv weight gradient on the tensor cores:
+//
+//     dW[co, ci] = sum_b sum_t dz[b, co, t] * a[b, ci, t]
+//
+// Both operands are activation rows [B, C, pitch] with time contiguous, i.e. BOTH are K-major for a GEMM whose
+// reduction dimension is (batch, time): A = dz tile [128 co x 64 t], B = a tile [BN ci x 64 t], SWIZZLE_128B boxes
+// straight from the 3-D tensor maps (frames >= T are zero-filled by TMA).  Grid = (Cout/128, Cin/BN, SPLIT): each CTA
+// reduces its slice of the batch into a TMEM accumulator and writes an fp32 partial [SPLIT, Cout, Cin]; the caller sums
+// the partials (deterministic, no atomics).  Same warp-specialised TMA / MMA / epilogue structure as pwgemm.cu.
+#include "ts_common.cuh"
+#include "sm100_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace ts {
+namespace wg {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16, BN = 256, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+
+struct Params {
+  CUtensorMap a, b;   // dz rows (t, co, b) box (64, 128, 1);  a rows (t, ci, b) box (64, 256, 1)
+  int Cout, Cin, T, B;
+  int bsplit;         // utterances per CTA
+  float* part;        // [SPLIT, Cout, Cin]
+};
+
+__global__ void __launch_bounds__(256, 1)
+pw_wgrad_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int b0 = split * p.bsplit, b1 = min(p.B, b0 + p.bsplit);
+  const int tchunks = (p.T + BK - 1) / BK;
+  const int num_k = (b1 - b0) * tchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.a);
+    ptx::prefetch_tensormap(&p.b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int kc = 0; kc < num_k; ++kc) {
+      const int s = kc % STAGES;
+      ptx::mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+      const int b = b0 + kc / tchunks, t0 = (kc % tchunks) * BK;
+      ptx::tma_load_3d(sa, &p.a, &full_bar[s], t0, m0, b);
+      ptx::tma_load_3d(sa + A_BYTES, &p.b, &full_bar[s], t0, n0, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    for (int kc = 0; kc < num_k; ++kc) {
+      const int s = kc % STAGES;
+      ptx::mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+      ptx::tc_fence_after();
+      const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        const uint64_t da = ptx::umma_desc(sa + k * 32, 0, 1024);
+        const uint64_t db = ptx::umma_desc(sb + k * 32, 0, 1024);
+        ptx::mma_bf16_ss(tmem_base, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+      }
+      ptx::mma_commit(&empty_bar[s]);
+    }
+    ptx::mma_commit(tmem_full);
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    if (num_k > 0) {
+      ptx::mbar_wait(tmem_full, 0);
+      ptx::tc_fence_after();
+    }
+    float* orow = p.part + ((size_t)split * p.Cout + m) * p.Cin;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      if (num_k > 0) {
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.Cin) orow[n0 + c0 + j] = __uint_as_float(v[j]);
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace wg
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B, int Cout, int Cin, int T,
+                           int nsplit, float* part, void* stream) {
+  TS_REQUIRE(dz && a && part, TS_ERR_INVALID, "ts_pw_wgrad: null pointer");
+  TS_REQUIRE(B > 0 && Cout > 0 && Cin > 0 && T > 0 && nsplit > 0 && nsplit <= B, TS_ERR_INVALID, "ts_pw_wgrad: bad sizes");
+  TS_REQUIRE(dz_pitch % 8 == 0 && a_pitch % 8 == 0 && dz_pitch >= T && a_pitch >= T, TS_ERR_INVALID,
+             "ts_pw_wgrad: pitches must be multiples of 8 frames and >= T");
+  wg::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = tma::make_3d_bf16(&p.a, dz, T, Cout, B, (uint64_t)dz_pitch * 2, (uint64_t)Cout * dz_pitch * 2, wg::BK, wg::BM,
+                              1)) != TS_OK)
+    return rc;
+  if ((rc = tma::make_3d_bf16(&p.b, a, T, Cin, B, (uint64_t)a_pitch * 2, (uint64_t)Cin * a_pitch * 2, wg::BK, wg::BN,
+                              1)) != TS_OK)
+    return rc;
+  p.Cout = Cout; p.Cin = Cin; p.T = T; p.B = B;
+  p.bsplit = ceil_div(B, nsplit);
+  p.part = part;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TS_CUDA(cudaFuncSetAttribute(wg::pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(Cout, wg::BM), ceil_div(Cin, wg::BN), nsplit);
+  wg::pw_wgrad_kernel<<<grid, 256, wg::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  TS_LAUNCH_CHECK("pw_wgrad_kernel");
+  return TS_OK;
+}

@@ -1,0 +1,283 @@
+// Training-step kernels around the two GEMM/Toeplitz engines (reference: BaseCTCModule.training_step,
+// src/thunder/module.py:102-127, with train()-mode modules of src/thunder/quartznet/blocks.py).
+//
+// In train() mode nn.BatchNorm1d(eps=1e-3, momentum=0.1) (quartznet/blocks.py:222) normalises with BATCH statistics over
+// all B x T positions (padded frames included -- the conv input is masked, the BatchNorm input is not), so BN can no
+// longer be folded into the GEMM.  Per sub-block the forward is
+//     a = dw(x)            (Toeplitz kernel)         z = W a        (pointwise GEMM, no shift / ReLU)
+//     stats(z)             row_stats_kernel          y = relu(BN(z) [+ BN_r(z_r)])   bn_apply_kernel
+// and the backward
+//     dym = dy * (y > 0);  sums(dym, dym*z)          bn_bwd_reduce_kernel
+//     dz = A dym + B z + C                           bn_bwd_apply_kernel
+//     dW = sum_{b,t} dz a^T (wgrad GEMM, pwgemm_wgrad.cu);  da = W^T dz (pointwise GEMM);  dw taps: dw_wgrad_kernel;
+//     dx = dw^T(da) (Toeplitz kernel with flipped taps).
+// All tensors are bf16 rows [B, C, pitch]; reductions accumulate in fp32 and are written per (b, c) row (deterministic),
+// the final sum over the batch is a tiny host-side torch reduction.
+#include "ts_common.cuh"
+
+namespace ts {
+namespace train {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    v[2 * h] = __uint_as_float(w[h] << 16);
+    v[2 * h + 1] = __uint_as_float(w[h] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    __nv_bfloat162 pr = __floats2bfloat162_rn(v[2 * h], v[2 * h + 1]);
+    o[h] = *reinterpret_cast<uint32_t*>(&pr);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+constexpr int RW = 8;  // warps per CTA for the row kernels
+
+// stats[row] = (sum_t z, sum_t z^2) over t < T, one warp per (b, c) row
+__global__ void __launch_bounds__(RW * 32)
+row_stats_kernel(const __nv_bfloat16* __restrict__ z, int T, int pitch, long long rows, float2* __restrict__ stats) {
+  const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* zr = z + row * pitch;
+  float s = 0.f, ss = 0.f;
+  for (int t = lane * 8; t < T; t += 256) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(zr + t), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (t + j < T) {
+        s += v[j];
+        ss = fmaf(v[j], v[j], ss);
+      }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) stats[row] = make_float2(s, ss);
+}
+
+// y = act(z * s[c] + h[c] (+ zr * sr[c] + hr[c])), frames t >= lens[b] (and the pad) stored as zero; 8 frames / thread
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ s,
+                                const float* __restrict__ h, const __nv_bfloat16* __restrict__ zr,
+                                const float* __restrict__ sr, const float* __restrict__ hr, int C, int T, int pitch,
+                                const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ y,
+                                long long rows) {
+  const long long row = blockIdx.x;
+  const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t >= pitch) return;
+  const int c = (int)(row % C);
+  const int lim = lens ? min(T, max(lens[row / C], 0)) : T;
+  float v[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), v);
+  const float sc = s[c], sh = h[c];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sc, sh);
+  if (zr != nullptr) {
+    unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), v);
+    const float sc2 = sr[c], sh2 = hr[c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += fmaf(v[j], sc2, sh2);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (relu) o[j] = fmaxf(o[j], 0.f);
+    if (t + j >= lim) o[j] = 0.f;
+  }
+  *reinterpret_cast<uint4*>(y + row * pitch + t) = pack8(o);
+}
+
+// sums[row] = (sum dym, sum dym*z, sum dym*zr) over t < T with dym = dy * (y > 0) (relu) or dy
+__global__ void __launch_bounds__(RW * 32)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                     const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr, int T, int pitch,
+                     long long rows, int relu, float* __restrict__ sums) {
+  const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int t = lane * 8; t < T; t += 256) {
+    float g[8], yy[8], zz[8], z2[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + row * pitch + t), g);
+    unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), zz);
+    if (relu) unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
+    if (zr != nullptr) unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), z2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t + j < T) {
+        const float d = (relu && !(yy[j] > 0.f)) ? 0.f : g[j];
+        s0 += d;
+        s1 = fmaf(d, zz[j], s1);
+        if (zr != nullptr) s2 = fmaf(d, z2[j], s2);
+      }
+    }
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    sums[row * 3 + 0] = s0;
+    sums[row * 3 + 1] = s1;
+    sums[row * 3 + 2] = s2;
+  }
+}
+
+// dz = A[c] dym + B[c] z + C[c]  (and dzr = Ar dym + Br zr + Cr) for t < T, pad frames zero
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                    const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr,
+                                    const float* __restrict__ coef, const float* __restrict__ coef_r, int C, int T,
+                                    int pitch, int relu, __nv_bfloat16* __restrict__ dz,
+                                    __nv_bfloat16* __restrict__ dzr, long long rows) {
+  const long long row = blockIdx.x;
+  const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t >= pitch) return;
+  const int c = (int)(row % C);
+  float g[8], yy[8], zz[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(dy + row * pitch + t), g);
+  unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), zz);
+  if (relu) {
+    unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(yy[j] > 0.f)) g[j] = 0.f;
+  }
+  const float a = coef[3 * c], b = coef[3 * c + 1], cc = coef[3 * c + 2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(a, g[j], fmaf(b, zz[j], cc)) : 0.f;
+  *reinterpret_cast<uint4*>(dz + row * pitch + t) = pack8(o);
+  if (zr != nullptr) {
+    unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), zz);
+    const float a2 = coef_r[3 * c], b2 = coef_r[3 * c + 1], c2 = coef_r[3 * c + 2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(a2, g[j], fmaf(b2, zz[j], c2)) : 0.f;
+    *reinterpret_cast<uint4*>(dzr + row * pitch + t) = pack8(o);
+  }
+}
+
+// Depthwise weight gradient: part[bchunk, c, k] = sum_{b in chunk} sum_t' da[b, c, t'] * xm[b, c, t' S + k D - P]
+// (xm = x masked at t >= len_in[b]; da is already zero beyond the output length).  One CTA per (channel, batch chunk);
+// thread k owns tap k; both rows are staged in shared memory as fp32.
+__global__ void __launch_bounds__(256)
+dw_wgrad_kernel(const __nv_bfloat16* __restrict__ da, int T_out, int pitch_out, const __nv_bfloat16* __restrict__ x,
+                int T_in, int pitch_in, const int32_t* __restrict__ len_in, int B, int C, int K, int S, int D, int P,
+                int bchunk, float* __restrict__ part) {
+  extern __shared__ float sm[];
+  float* sx = sm;               // [pitch_in + 2 * halo] with halo = P on the left
+  float* sd = sm + pitch_in + 2 * (K * D + 8);
+  const int c = blockIdx.x, chunk = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int halo = K * D + 8;
+  float acc = 0.f;
+  const int b0 = chunk * bchunk, b1 = min(B, b0 + bchunk);
+  for (int b = b0; b < b1; ++b) {
+    const long long row = (long long)b * C + c;
+    int lin = T_in;
+    if (len_in != nullptr) lin = min(lin, max(len_in[b], 0));
+    __syncthreads();
+    for (int i = tid; i < pitch_in + 2 * halo; i += blockDim.x) {
+      const int t = i - halo;
+      sx[i] = (t >= 0 && t < lin) ? __bfloat162float(x[row * pitch_in + t]) : 0.f;
+    }
+    for (int i = tid; i < pitch_out; i += blockDim.x)
+      sd[i] = (i < T_out) ? __bfloat162float(da[row * pitch_out + i]) : 0.f;
+    __syncthreads();
+    if (tid < K) {
+      const float* xs = sx + halo + tid * D - P;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int t = 0;
+      for (; t + 4 <= T_out; t += 4) {
+        a0 = fmaf(sd[t], xs[t * S], a0);
+        a1 = fmaf(sd[t + 1], xs[(t + 1) * S], a1);
+        a2 = fmaf(sd[t + 2], xs[(t + 2) * S], a2);
+        a3 = fmaf(sd[t + 3], xs[(t + 3) * S], a3);
+      }
+      for (; t < T_out; ++t) a0 = fmaf(sd[t], xs[t * S], a0);
+      acc += (a0 + a1) + (a2 + a3);
+    }
+  }
+  if (tid < K) part[((size_t)chunk * C + c) * K + tid] = acc;
+}
+
+}  // namespace train
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" int ts_row_stats(const void* z, int B, int C, int T, int pitch, float* stats, void* stream) {
+  TS_REQUIRE(z && stats, TS_ERR_INVALID, "ts_row_stats: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_row_stats: bad sizes");
+  const long long rows = (long long)B * C;
+  train::row_stats_kernel<<<(unsigned)ceil_div64(rows, train::RW), train::RW * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)z, T, pitch, rows, (float2*)stats);
+  TS_LAUNCH_CHECK("row_stats_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_apply(const void* z, const float* scale, const float* shift, const void* zr, const float* scale_r,
+                           const float* shift_r, int B, int C, int T, int pitch, const int32_t* lens, int relu, void* y,
+                           void* stream) {
+  TS_REQUIRE(z && scale && shift && y, TS_ERR_INVALID, "ts_bn_apply: null pointer");
+  TS_REQUIRE((zr == nullptr) == (scale_r == nullptr) && (zr == nullptr) == (shift_r == nullptr), TS_ERR_INVALID,
+             "ts_bn_apply: residual operands disagree");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_apply: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_apply: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
+  train::bn_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift,
+                                                                 (const __nv_bfloat16*)zr, scale_r, shift_r, C, T, pitch,
+                                                                 lens, relu, (__nv_bfloat16*)y, rows);
+  TS_LAUNCH_CHECK("bn_apply_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, const void* zr, int B, int C, int T,
+                                int pitch, int relu, float* sums, void* stream) {
+  TS_REQUIRE(dy && z && sums && (!relu || y), TS_ERR_INVALID, "ts_bn_bwd_reduce: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_reduce: bad sizes");
+  const long long rows = (long long)B * C;
+  train::bn_bwd_reduce_kernel<<<(unsigned)ceil_div64(rows, train::RW), train::RW * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, T, pitch, rows,
+      relu, sums);
+  TS_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, const void* zr, const float* coef,
+                               const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr,
+                               void* stream) {
+  TS_REQUIRE(dy && z && coef && dz && (!relu || y), TS_ERR_INVALID, "ts_bn_bwd_apply: null pointer");
+  TS_REQUIRE((zr == nullptr) == (coef_r == nullptr) && (zr == nullptr) == (dzr == nullptr), TS_ERR_INVALID,
+             "ts_bn_bwd_apply: residual operands disagree");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_apply: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_bwd_apply: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
+  train::bn_bwd_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, coef, coef_r, C,
+      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows);
+  TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in,
+                           const int32_t* len_in, int B, int C, int K, int S, int D, int P, int bchunk, float* part,
+                           void* stream) {
+  TS_REQUIRE(da && x && part, TS_ERR_INVALID, "ts_dw_wgrad: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && K > 0 && K <= 256 && S > 0 && D > 0 && P >= 0 && bchunk > 0, TS_ERR_INVALID,
+             "ts_dw_wgrad: bad sizes (K <= 256)");
+  TS_REQUIRE((T_out - 1) * S + (K - 1) * D - P < pitch_in + K * D + 8, TS_ERR_INVALID, "ts_dw_wgrad: window exceeds row");
+  const size_t smem = (size_t)(pitch_in + 2 * (K * D + 8) + pitch_out) * sizeof(float);
+  TS_REQUIRE(smem <= 200 * 1024, TS_ERR_UNSUPPORTED, "ts_dw_wgrad: rows too long for shared memory");
+  if (smem > 48 * 1024)
+    TS_CUDA(cudaFuncSetAttribute(train::dw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(C, ceil_div(B, bchunk));
+  train::dw_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)da, T_out, pitch_out,
+                                                                    (const __nv_bfloat16*)x, T_in, pitch_in, len_in, B, C,
+                                                                    K, S, D, P, bchunk, part);
+  TS_LAUNCH_CHECK("dw_wgrad_kernel");
+  return TS_OK;
+}
