@@ -38,11 +38,13 @@ WORKLOADS = {
                  64, 20, 64),
     "quartznet15x5": ("QuartzNet 15x5 inference bf16, batch 256 x 15 s synthetic audio", 256, 15, 64),
     "citrinet1024": ("Citrinet-1024 with SqueezeExcite inference bf16, 1024-token vocab, batch 128 x 20 s", 128, 20, 80),
+    "quartznet15x5_train": ("QuartzNet 15x5 training step (forward + backward + CTC loss + AdamW) with NCCL gradient "
+                            "allreduce, per-GPU batch 32 x 15 s", 32, 15, 64),
 }
 
 
 #: bounded CPU sample (utterances per step) for the cpu_baseline / --impl reference legs: ~5-20 s of host work in total
-CPU_SAMPLE_BATCH = {"features": 64, "quartznet15x5": 16, "citrinet1024": 4}
+CPU_SAMPLE_BATCH = {"features": 64, "quartznet15x5": 16, "citrinet1024": 4, "quartznet15x5_train": 4}
 
 
 def traffic_per_launch(kernel: str, workload: str):

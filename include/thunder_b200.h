@@ -169,6 +169,28 @@ int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B,
 int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
                 int B, int C, int K, int S, int D, int P, int bchunk, float* part, void* stream);
 
+/* BatchNorm train()-mode statistics from the per-utterance partial sums of ts_row_stats (part [NB, C, 2]):
+ * mean, biased variance over n = B*T positions -> scale = gamma * inv, shift = beta - mean * scale, mean, inv = rsqrt(var +
+ * eps); running_mean / running_var (nullable) are updated in place with `momentum` and the UNBIASED variance, as
+ * nn.BatchNorm1d does (quartznet/blocks.py:222-228).  Everything on the device: no host round trip, graph-capturable. */
+int ts_bn_finalize(const float* part, int NB, int C, double n, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                   float* inv, void* stream);
+/* BatchNorm backward coefficients from the partial sums of ts_bn_bwd_reduce (part [NB, C, 3]; `which` = 1 for the main
+ * branch (sum dym*z), 2 for the residual branch (sum dym*zr)): dbeta = sum dym, dgamma = inv (sum dym*z - mean sum dym),
+ * coef[c] = (a, b, c0) with dz = a dym + b z + c0 (see ts_bn_bwd_apply) */
+int ts_bn_bwd_coef(const float* part, int NB, int C, int which, double n, const float* gamma, const float* mean,
+                   const float* inv, float* dgamma, float* dbeta, float* coef, void* stream);
+/* CTC loss with fused log-softmax and its gradient w.r.t. the logits (calculate_ctc, src/thunder/ctc_loss.py:15-47:
+ * log_softmax -> F.ctc_loss(blank, reduction="mean", zero_infinity=True)).  logits: f32 rows [B, V, pitch] (pitch >= T);
+ * in_len: int32 [B] encoder output lengths; targets int64 [B, Lmax], tgt_len int64 [B].  loss[b] = nll_b / max(tgt_len_b,
+ * 1) (0 when infinite); the reference's loss is mean_b loss[b].  grad: bf16 rows [B, Vp, grad_pitch] (Vp >= V; rows >= V
+ * untouched; grad_pitch a multiple of 8; frames >= T zeroed) =
+ * gscale * d mean_b(loss) / d logits.  scratch: >= 2*B*T*Sp + B*T + B floats with Sp = round_up(2*Lmax+1, 4). */
+int ts_ctc_loss(const float* logits, int B, int V, int T, int pitch, const int32_t* in_len, const int64_t* targets,
+                int Lmax, const int64_t* tgt_len, int blank, float gscale, float* scratch, long long scratch_floats,
+                float* loss, void* grad, int Vp, int grad_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,34 @@ def make_workload(name: str, batch: int, samples: int, nfilt: int):
                 return features(x, lens, nfilt=nfilt, fb=fb)
 
         return feat_step, f"B={batch} x {samples / 16000:.0f} s, torch CPU fp32"
+    if name == "quartznet15x5_train":
+        # BaseCTCModule.training_step + AdamW (src/thunder/module.py:102-127, :32): features under no_grad, train()-mode
+        # encoder, decoder, calculate_ctc, backward, optimiser step -- all torch CPU fp32 autograd
+        cfgs = R.quartznet_cfgs(repeat_blocks=3)
+        st = to_torch(synth.encoder_state(synth.quartznet_block_list(repeat_blocks=3), seed=0))
+        dec = to_torch(synth.decoder_state(1024, 29, seed=1))
+        params = []
+        for k, v in list(st.items()) + list(dec.items()):
+            if v.dtype.is_floating_point and "running" not in k:
+                params.append(v.requires_grad_(True))
+        opt = torch.optim.AdamW(params, lr=1e-4)
+        rng = np.random.Generator(np.random.PCG64(99))
+        L = 120
+        y = torch.from_numpy(rng.integers(0, 28, (batch, L)).astype(np.int64))
+        ylen = torch.from_numpy(rng.integers(L // 2, L + 1, batch).astype(np.int64))
+        rl = torch.from_numpy(synth.ragged_lengths(batch, samples, 7))
+
+        def train_step():
+            opt.zero_grad()
+            with torch.no_grad():
+                f, fl = features(x, rl, nfilt=nfilt)
+            e, el = encoder(f, fl, cfgs, st, train=True)
+            loss = ctc_loss(F.conv1d(e, dec["weight"], dec["bias"]), y, el, ylen, 28)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+
+        return train_step, f"B={batch} x {samples / 16000:.0f} s training step (fwd+bwd+CTC+AdamW), torch CPU fp32 autograd"
     if name == "quartznet15x5":
         cfgs = R.quartznet_cfgs(repeat_blocks=3)
         st = to_torch(synth.encoder_state(synth.quartznet_block_list(repeat_blocks=3), seed=0))

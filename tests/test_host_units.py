@@ -203,6 +203,14 @@ calls = []
 def fake_predict(x):                       # stands in for CTCModule.predict on this rank's shard
     calls.append(x.shape[0])
     return ["utt%d" % int(r[0].item() // 4) for r in x]
+# training path: one flat gradient buffer, averaged in place over the ranks
+from thunder_speech_b200.parallel import allreduce_mean_, flat_grad_views
+lin = torch.nn.Linear(3, 2)
+flat = flat_grad_views(lin.parameters())
+assert flat.numel() == 8 and lin.weight.grad.data_ptr() == flat.data_ptr()
+lin.weight.grad.fill_(1.0 + dist.get_rank()); lin.bias.grad.fill_(10.0 * dist.get_rank())
+allreduce_mean_(flat)
+assert torch.allclose(lin.weight.grad, torch.full((2, 3), 1.5)) and torch.allclose(lin.bias.grad, torch.full((2,), 5.0))
 out = sharded_predict(fake_predict, audio)
 assert out == ["utt%d" % i for i in range(7)], out
 lo, hi = shard_bounds(7, 2, dist.get_rank())
@@ -213,7 +221,8 @@ print("rank", sys.argv[3], "ok")
 
 
 def test_sharded_predict_world_size_2_gloo(tmp_path):
-    """N > 1 path on CPU: two gloo ranks shard a batch with no data-path collective and gather the transcripts."""
+    """N > 1 paths on CPU: two gloo ranks shard a batch with no data-path collective and gather the transcripts; the
+    training step's flat gradient buffer is averaged in place."""
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
     import socket

@@ -265,3 +265,89 @@ def test_block_gradients_vs_bf16_storage_oracle(cin, cout, K, rep, B, T, res):
     for k, p in blk.named_parameters():
         e = l2(p.grad.cpu().numpy(), stt[k].grad.numpy())
         assert e < tol, (k, e)
+
+
+@pytest.mark.parametrize("B,V,T,Lmax,seed", [(6, 29, 101, 12, 0), (3, 29, 376, 120, 1), (4, 5, 40, 30, 2), (2, 200, 33, 7, 3)])
+def test_ctc_loss_kernel_vs_torch(B, V, T, Lmax, seed):
+    """ts_ctc_loss against log_softmax + F.ctc_loss(reduction="mean", zero_infinity=True) (src/thunder/ctc_loss.py:15-47)
+    in float64 on the CPU: per-utterance loss and the gradient w.r.t. the logits.  Covers ragged input / target lengths,
+    repeated labels (forced blanks), an empty target and an infeasible utterance (target longer than the input: infinite
+    loss -> zeroed)."""
+    from thunder_speech_b200.train import ctc_loss
+
+    rng = np.random.default_rng(seed)
+    blank = V - 1
+    logits = (3.0 * rng.standard_normal((B, V, T))).astype(np.float32)
+    y = rng.integers(0, V - 1, (B, Lmax)).astype(np.int64)
+    y[0, : Lmax // 2] = y[0, 0]                        # long run of a repeated label
+    tl = rng.integers(1, Lmax + 1, B).astype(np.int64)
+    il = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    il[0] = T
+    tl[0] = min(Lmax, T // 3)
+    if B > 2:
+        tl[1] = 0                                      # empty transcript
+        il[2], tl[2] = 4, min(Lmax, 6)                 # infeasible -> inf -> zero_infinity
+    for b in range(B):                                 # keep the others feasible
+        if not (B > 2 and b == 2):
+            tl[b] = min(tl[b], il[b] // 2)
+    # reference (float64)
+    lt = torch.from_numpy(logits).double().requires_grad_(True)
+    lp = torch.nn.functional.log_softmax(lt.permute(2, 0, 1), dim=2)
+    per = torch.nn.functional.ctc_loss(lp, torch.from_numpy(y), torch.from_numpy(il).long(), torch.from_numpy(tl), blank=blank,
+                                       reduction="none", zero_infinity=True)
+    ref_loss = per / torch.from_numpy(tl).clamp_min(1)
+    ref_loss.mean().backward()
+    # kernel
+    pitch = ops.row_pitch(T)
+    lg = torch.zeros((B, V, pitch), dtype=torch.float32, device="cuda")
+    lg[:, :, :T] = torch.from_numpy(logits).cuda()
+    lg[:, :, T:] = float("nan")                        # the pad must never be read
+    loss, grad = ctc_loss(lg, T, torch.from_numpy(il).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(tl).cuda(), blank,
+                          Vp=(V + 63) // 64 * 64)
+    torch.cuda.synchronize()
+    assert np.allclose(loss.cpu().numpy(), ref_loss.detach().numpy(), rtol=2e-5, atol=1e-5), (loss.cpu().numpy(), ref_loss)
+    g = grad.float().cpu().numpy()
+    assert np.all(g[:, V:, :] == 0) and np.all(g[:, :, T:] == 0)
+    gr = lt.grad.numpy()
+    # bf16 output: 2^-9 relative per element
+    assert np.abs(g[:, :V, :T] - gr).max() <= 2 ** -8 * np.abs(gr).max() + 1e-9
+    assert l2(g[:, :V, :T], gr) < 4e-3
+    if B > 2:
+        assert loss[2].item() == 0.0 and np.all(g[2] == 0)
+
+
+def test_bn_finalize_and_bwd_coef_kernels():
+    from thunder_speech_b200.train import bn_bwd_coef, bn_finalize
+
+    rng = np.random.default_rng(5)
+    NB, C, n = 7, 300, 7 * 123
+    part = rng.standard_normal((NB, C, 2)).astype(np.float32)
+    part[:, :, 1] = np.abs(part[:, :, 1]) * 50 + 30
+    bn = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.1).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)))
+        bn.bias.copy_(torch.from_numpy(rng.standard_normal(C).astype(np.float32)))
+        bn.running_mean.copy_(torch.from_numpy(rng.standard_normal(C).astype(np.float32)))
+    rm0, rv0 = bn.running_mean.cpu().numpy().astype(np.float64), bn.running_var.cpu().numpy().astype(np.float64)
+    scale, shift, mean, inv = bn_finalize(torch.from_numpy(part).cuda(), n, bn, True)
+    s = part.astype(np.float64).sum(0)
+    m = s[:, 0] / n
+    var = np.maximum(s[:, 1] / n - m * m, 0)
+    iv = 1 / np.sqrt(var + 1e-3)
+    g, b = bn.weight.detach().cpu().numpy().astype(np.float64), bn.bias.detach().cpu().numpy().astype(np.float64)
+    assert rel_err(mean.cpu().numpy(), m)[0] < 1e-6 and rel_err(inv.cpu().numpy(), iv)[0] < 1e-6
+    assert rel_err(scale.cpu().numpy(), g * iv)[0] < 1e-6 and rel_err(shift.cpu().numpy(), b - m * g * iv)[0] < 1e-6
+    assert rel_err(bn.running_mean.cpu().numpy(), 0.9 * rm0 + 0.1 * m)[0] < 1e-6
+    assert rel_err(bn.running_var.cpu().numpy(), 0.9 * rv0 + 0.1 * var * n / (n - 1))[0] < 1e-6
+    part3 = rng.standard_normal((NB, C, 3)).astype(np.float32)
+    for which in (1, 2):
+        bn.weight.grad = None
+        bn.bias.grad = None
+        coef = bn_bwd_coef(torch.from_numpy(part3).cuda(), which, n, bn, mean, inv).cpu().numpy()
+        s3 = part3.astype(np.float64).sum(0)
+        dg = iv * (s3[:, which] - m * s3[:, 0])
+        a = g * iv
+        bb = -g * iv * iv * dg / n
+        cc = -a * s3[:, 0] / n - bb * m
+        assert rel_err(bn.weight.grad.cpu().numpy(), dg)[0] < 1e-5 and rel_err(bn.bias.grad.cpu().numpy(), s3[:, 0])[0] < 1e-6
+        assert rel_err(coef, np.stack([a, bb, cc], 1))[0] < 1e-5

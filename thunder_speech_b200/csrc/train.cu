@@ -263,12 +263,103 @@ extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, con
   return TS_OK;
 }
 
+namespace ts {
+namespace train {
+
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int NB, int C, double n, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ inv_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < NB; ++b) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)b * C + c) * 2);
+    s0 += v.x;
+    s1 += v.y;
+  }
+  const double mean = s0 / n;
+  double var = s1 / n - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const double inv = 1.0 / sqrt(var + (double)eps);
+  const double sc = (double)gamma[c] * inv;
+  scale[c] = (float)sc;
+  shift[c] = (float)((double)beta[c] - mean * sc);
+  mean_out[c] = (float)mean;
+  inv_out[c] = (float)inv;
+  if (rmean != nullptr) {
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(var * n / (n > 1.0 ? n - 1.0 : 1.0));
+  }
+}
+
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ part, int NB, int C, int which, double n,
+                                   const float* __restrict__ gamma, const float* __restrict__ mean,
+                                   const float* __restrict__ inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                   float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < NB; ++b) {
+    const float* p = part + ((size_t)b * C + c) * 3;
+    s0 += p[0];
+    s1 += p[which];
+  }
+  const double m = mean[c], iv = inv[c], g = gamma[c];
+  const double dg = iv * (s1 - m * s0);
+  const double a = g * iv;
+  const double b2 = -g * iv * iv * dg / n;
+  const double c0 = -a * s0 / n - b2 * m;
+  dgamma[c] = (float)dg;
+  dbeta[c] = (float)s0;
+  coef[c * 3 + 0] = (float)a;
+  coef[c * 3 + 1] = (float)b2;
+  coef[c * 3 + 2] = (float)c0;
+}
+
+}  // namespace train
+}  // namespace ts
+
+extern "C" int ts_bn_finalize(const float* part, int NB, int C, double n, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                              float* mean, float* inv, void* stream) {
+  TS_REQUIRE(part && gamma && beta && scale && shift && mean && inv, TS_ERR_INVALID, "ts_bn_finalize: null pointer");
+  TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID,
+             "ts_bn_finalize: bad sizes");
+  train::bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(part, NB, C, n, gamma, beta, eps, momentum,
+                                                                               running_mean, running_var, scale, shift,
+                                                                               mean, inv);
+  TS_LAUNCH_CHECK("bn_finalize_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_coef(const float* part, int NB, int C, int which, double n, const float* gamma, const float* mean,
+                              const float* inv, float* dgamma, float* dbeta, float* coef, void* stream) {
+  TS_REQUIRE(part && gamma && mean && inv && dgamma && dbeta && coef, TS_ERR_INVALID, "ts_bn_bwd_coef: null pointer");
+  TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (which == 1 || which == 2), TS_ERR_INVALID, "ts_bn_bwd_coef: bad arguments");
+  train::bn_bwd_coef_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(part, NB, C, which, n, gamma, mean, inv,
+                                                                               dgamma, dbeta, coef);
+  TS_LAUNCH_CHECK("bn_bwd_coef_kernel");
+  return TS_OK;
+}
+
+int launch_dw_wgrad_tiled(const __nv_bfloat16* da, int T_out, int pitch_out, const __nv_bfloat16* x, int T_in, int pitch_in,
+                          const int32_t* len_in, int B, int C, int K, int D, int P, int bchunk, float* part,
+                          cudaStream_t st);
+
 extern "C" int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in,
                            const int32_t* len_in, int B, int C, int K, int S, int D, int P, int bchunk, float* part,
                            void* stream) {
   TS_REQUIRE(da && x && part, TS_ERR_INVALID, "ts_dw_wgrad: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && K > 0 && K <= 256 && S > 0 && D > 0 && P >= 0 && bchunk > 0, TS_ERR_INVALID,
              "ts_dw_wgrad: bad sizes (K <= 256)");
+  TS_REQUIRE(pitch_in % 8 == 0 && pitch_out % 8 == 0 && pitch_in >= T_in && pitch_out >= T_out, TS_ERR_INVALID,
+             "ts_dw_wgrad: pitches must be multiples of 8 frames and >= T");
+  if (S == 1) {   // register-tiled kernel (dwwgrad.cu); the kernel below is the generic fallback (strided stem)
+    const int rc = launch_dw_wgrad_tiled((const __nv_bfloat16*)da, T_out, pitch_out, (const __nv_bfloat16*)x, T_in, pitch_in,
+                                         len_in, B, C, K, D, P, bchunk, part, (cudaStream_t)stream);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   TS_REQUIRE((T_out - 1) * S + (K - 1) * D - P < pitch_in + K * D + 8, TS_ERR_INVALID, "ts_dw_wgrad: window exceeds row");
   const size_t smem = (size_t)(pitch_in + 2 * (K * D + 8) + pitch_out) * sizeof(float);
   TS_REQUIRE(smem <= 200 * 1024, TS_ERR_UNSUPPORTED, "ts_dw_wgrad: rows too long for shared memory");

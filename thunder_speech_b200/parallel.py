@@ -35,3 +35,27 @@ def sharded_predict(predict: Callable[[torch.Tensor], List[str]], audio: torch.T
     for p in parts:
         out.extend(p)
     return out
+
+
+def flat_grad_views(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
+    """Allocates ONE flat fp32 buffer holding every parameter's gradient and points each ``param.grad`` at its slice, so
+    that data-parallel training (BASELINE config 5) averages gradients with a single in-place collective and no packing."""
+    params = list(params)
+    flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
+    off = 0
+    for p in params:
+        if p.dtype != torch.float32:
+            raise TypeError("flat_grad_views: fp32 master weights expected")
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """In-place mean of `flat` over all ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests); no-op when
+    torch.distributed is not initialised or world_size == 1.  This is what DDP does for the reference's training_step."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    return flat

@@ -136,5 +136,106 @@ class ModelWorkload:
         return out
 
 
+class TrainWorkload:
+    """bench.py workload (BASELINE config 5): one optimisation step of QuartzNet 15x5 -- features, train()-mode forward,
+    CTC loss, backward, gradient all-reduce (NCCL when world > 1), AdamW -- on a per-GPU batch of synthetic audio with
+    random 29-character transcripts."""
+
+    NBUF = 2
+    dtype = "bf16"
+    LABEL_LEN = 120   # characters per 15 s utterance (~8 per second)
+
+    def __init__(self, name, B, N, nfilt, dev, rank):
+        from .train import CTCTrainStep
+
+        self.name, self.B, self.N, self.dev = name, B, N, dev
+        self.model = build_model("quartznet15x5", dev)
+        self.model.encoder.train()
+        self.model.decoder.train()
+        self.trainer = CTCTrainStep(self.model, lr=1e-4)
+        rng = np.random.Generator(np.random.PCG64(99 + rank))
+        self.host_audio = torch.from_numpy(synth.audio(B, N, 1234 + rank, "noise")).pin_memory()
+        self.host_lens = torch.from_numpy(synth.ragged_lengths(B, N, 7 + rank)).pin_memory()
+        self.host_y = torch.from_numpy(rng.integers(0, 28, (B, self.LABEL_LEN)).astype(np.int64)).pin_memory()
+        self.host_ylen = torch.from_numpy(rng.integers(self.LABEL_LEN // 2, self.LABEL_LEN + 1, B).astype(np.int64)).pin_memory()
+        self.audio = [(self.host_audio.to(dev) * (1.0 + 0.01 * i)).contiguous() for i in range(self.NBUF)]
+        self.lens, self.y, self.ylen = self.host_lens.to(dev), self.host_y.to(dev), self.host_ylen.to(dev)
+        self.stage = torch.empty((B, N), dtype=torch.float32, device=dev)
+        self.h2d_bytes = B * N * 4 + B * 8 + self.host_y.numel() * 8 + B * 8
+        self.d2h_bytes = 4
+        self.l2_note = ("the step's saved activations (several GB) exceed the 126 MB L2; audio rotates over "
+                        f"{self.NBUF} buffers")
+        self.last_loss = None
+
+    def graph_launches(self) -> int:
+        return self.trainer.graph_launches()
+
+    def step_device(self, i):
+        self.last_loss = self.trainer.step(self.audio[i % self.NBUF], self.lens, self.y, self.ylen)
+        return self.last_loss
+
+    def step_host(self, i):
+        self.stage.copy_(self.host_audio, non_blocking=True)
+        lens = self.host_lens.to(self.dev, non_blocking=True)
+        y = self.host_y.to(self.dev, non_blocking=True)
+        ylen = self.host_ylen.to(self.dev, non_blocking=True)
+        return float(self.trainer.step(self.stage, lens, y, ylen).item())
+
+    def run_host(self, steps):
+        for i in range(steps):
+            self.step_host(i)
+
+    def roofline(self, steps):
+        """Eager step with CUDA events around every kernel launch of this library (torch's own kernels -- decoder,
+        log_softmax, CTC loss, AdamW, the [C]-vector arithmetic -- are not in the list; their share is reported as
+        `other_ms_per_step` = step time - sum of ours)."""
+        n = 2
+        tr = self.trainer
+        fb = lambda i: tr._forward_backward(self.audio[i % self.NBUF], self.lens, self.y, self.ylen, update_running=False)
+        fb(0)
+        torch.cuda.synchronize()
+        # graph replay time of the same work (what the timed region runs), for the share-of-step column
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(n):   # forward + loss + backward only: no collective on this rank-0-only pass
+            tr.loss_and_grads(self.audio[i % self.NBUF], self.lens, self.y, self.ylen)
+        g1.record()
+        torch.cuda.synchronize()
+        step_ms = g0.elapsed_time(g1) / n
+        ops.PROFILE = []
+        try:
+            for i in range(n):
+                # keep the GPU busy while the CPU queues the ~1400 launches of the eager pass (see ModelWorkload.roofline)
+                torch.cuda._sleep(int(150e6))
+                fb(i)
+            torch.cuda.synchronize()
+            recs = ops.PROFILE
+        finally:
+            ops.PROFILE = None
+        agg = {}
+        for name, meta, a0, a1 in recs:
+            a = agg.setdefault(name, dict(ms=0.0, bytes=0, flops=0, calls=0))
+            a["ms"] += a0.elapsed_time(a1)
+            a["bytes"] += meta["bytes"]
+            a["flops"] += meta["flops"]
+            a["calls"] += 1
+        total_ms = sum(a["ms"] for a in agg.values())
+        shares = {k: {"ms_per_step": a["ms"] / n, "share_of_step": a["ms"] / n / step_ms, "launches_per_step": a["calls"] // n,
+                      "GBps": a["bytes"] / (a["ms"] * 1e-3) / 1e9, "TFLOPs": a["flops"] / (a["ms"] * 1e-3) / 1e12}
+                  for k, a in agg.items()}
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        a = agg[top]
+        tensor = top in ("pw_gemm", "pw_wgrad")
+        out = {"kernel": {"pw_gemm": "pw_gemm_pair_kernel", "pw_wgrad": "pw_wgrad_kernel", "dw_conv": "dw_tma_kernel"}.get(top, top + "_kernel"),
+               "bound": "tensor" if tensor else "hbm",
+               "achieved": (a["flops"] / (a["ms"] * 1e-3) / 1e12) if tensor else (a["bytes"] / (a["ms"] * 1e-3) / 1e9),
+               "unit": "TFLOP/s" if tensor else "GB/s", "avg_kernel_ms": a["ms"] / a["calls"],
+               "launches_per_step": a["calls"] // n, "traffic": None, "per_kernel": shares,
+               "other_ms_per_step": step_ms - total_ms / n, "graph_step_ms": step_ms}
+        return out
+
+
 def make_bench_workload(name, B, N, nfilt, dev, rank):
+    if name == "quartznet15x5_train":
+        return TrainWorkload(name, B, N, nfilt, dev, rank)
     return ModelWorkload(name, B, N, nfilt, dev, rank)

@@ -25,6 +25,7 @@ from torch import Tensor, nn
 
 from . import _lib, ops
 from .blocks import conv_out_length
+from .parallel import allreduce_mean_, flat_grad_views
 
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.1
@@ -43,56 +44,125 @@ def row_stats(z: Tensor, T: int) -> Tensor:
     """[C, 2] = (sum z, sum z^2) over batch and t < T."""
     B, C, pitch = z.shape
     st = torch.empty((B, C, 2), device=z.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_row_stats(_p(z), B, C, T, pitch, _p(st), _stream()), "ts_row_stats")
+    with ops._timed("row_stats", bytes=B * C * T * 2, flops=0):
+        _lib.check(_lib.lib().ts_row_stats(_p(z), B, C, T, pitch, _p(st), _stream()), "ts_row_stats")
     return st.sum(0, dtype=torch.float64)
+
+
+def row_stats_partial(z: Tensor, T: int) -> Tensor:
+    """[B, C, 2] per-utterance (sum z, sum z^2) over t < T (summed over B by ts_bn_finalize)."""
+    B, C, pitch = z.shape
+    st = torch.empty((B, C, 2), device=z.device, dtype=torch.float32)
+    with ops._timed("row_stats", bytes=B * C * T * 2, flops=0):
+        _lib.check(_lib.lib().ts_row_stats(_p(z), B, C, T, pitch, _p(st), _stream()), "ts_row_stats")
+    return st
+
+
+def bn_finalize(part: Tensor, n: int, bn: nn.BatchNorm1d, update_running: bool):
+    """(scale, shift, mean, inv) f32 [C] from the partial sums, on the device; updates the running statistics in place like
+    nn.BatchNorm1d(momentum) does in train() (unbiased variance for the running estimate)."""
+    NB, C, _ = part.shape
+    out = torch.empty((4, C), device=part.device, dtype=torch.float32)
+    upd = update_running and bn.track_running_stats
+    m = bn.momentum if bn.momentum is not None else BN_MOMENTUM
+    _lib.check(_lib.lib().ts_bn_finalize(_p(part), NB, C, float(n), _p(bn.weight), _p(bn.bias), float(bn.eps), float(m),
+                                         _p(bn.running_mean) if upd else None, _p(bn.running_var) if upd else None,
+                                         _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _stream()), "ts_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_bwd_coef(part: Tensor, which: int, n: int, bn: nn.BatchNorm1d, mean: Tensor, inv: Tensor) -> Tensor:
+    """coef [C, 3] of dz = a dym + b z + c; writes dgamma / dbeta straight into ``bn.weight.grad`` / ``bn.bias.grad``."""
+    NB, C, _ = part.shape
+    coef = torch.empty((C, 3), device=part.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ts_bn_bwd_coef(_p(part), NB, C, which, float(n), _p(bn.weight), _p(mean), _p(inv),
+                                         _p(_grad(bn.weight)), _p(_grad(bn.bias)), _p(coef), _stream()), "ts_bn_bwd_coef")
+    return coef
+
+
+def ctc_loss(logits: Tensor, T: int, in_len: Tensor, targets: Tensor, tgt_len: Tensor, blank: int, Vp: int = 64,
+             gscale: float = 1.0) -> Tuple[Tensor, Tensor]:
+    """(loss [B] = nll_b / max(target_len_b, 1), zero when infinite;  d mean(loss) / d logits as bf16 rows [B, Vp, pitch])
+    from f32 logit rows [B, V, pitch]: log_softmax + F.ctc_loss(reduction="mean", zero_infinity=True) and its backward."""
+    B, V, pitch = logits.shape
+    gp = ops.row_pitch(T)
+    assert logits.dtype == torch.float32 and targets.dtype == torch.int64 and tgt_len.dtype == torch.int64
+    assert in_len.dtype == torch.int32
+    Lmax = targets.shape[1]
+    Sp = (2 * Lmax + 1 + 3) // 4 * 4
+    nfl = 2 * B * T * Sp + B * T + B
+    scratch = torch.empty((nfl,), device=logits.device, dtype=torch.float32)
+    loss = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    grad = torch.zeros((B, max(Vp, V), gp), device=logits.device, dtype=torch.bfloat16)
+    with ops._timed("ctc_loss", bytes=B * V * T * 4 + 2 * 2 * B * T * Sp * 4, flops=0):
+        _lib.check(_lib.lib().ts_ctc_loss(_p(logits), B, V, T, pitch, _p(in_len), _p(targets.contiguous()), Lmax,
+                                          _p(tgt_len), int(blank), float(gscale), _p(scratch), nfl, _p(loss), _p(grad),
+                                          grad.shape[1], gp, _stream()), "ts_ctc_loss")
+    return loss, grad
 
 
 def bn_apply(z, scale, shift, zr, scale_r, shift_r, T, lens, relu=True) -> Tensor:
     B, C, pitch = z.shape
     y = torch.empty_like(z)
-    _lib.check(_lib.lib().ts_bn_apply(_p(z), _p(scale), _p(shift), _p(zr), _p(scale_r), _p(shift_r), B, C, T, pitch,
-                                      _p(lens), int(relu), _p(y), _stream()), "ts_bn_apply")
+    with ops._timed("bn_apply", bytes=B * C * T * 2 * (3 if zr is not None else 2), flops=0):
+        _lib.check(_lib.lib().ts_bn_apply(_p(z), _p(scale), _p(shift), _p(zr), _p(scale_r), _p(shift_r), B, C, T, pitch,
+                                          _p(lens), int(relu), _p(y), _stream()), "ts_bn_apply")
     return y
 
 
-def bn_bwd_reduce(dy, y, z, zr, T, relu=True) -> Tensor:
+def bn_bwd_reduce(dy, y, z, zr, T, relu=True, partial: bool = False) -> Tensor:
     B, C, pitch = z.shape
     sums = torch.empty((B, C, 3), device=z.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_bn_bwd_reduce(_p(dy), _p(y), _p(z), _p(zr), B, C, T, pitch, int(relu), _p(sums), _stream()),
-               "ts_bn_bwd_reduce")
-    return sums.sum(0, dtype=torch.float64)
+    with ops._timed("bn_bwd_reduce", bytes=B * C * T * 2 * (4 if zr is not None else 3), flops=0):
+        _lib.check(_lib.lib().ts_bn_bwd_reduce(_p(dy), _p(y), _p(z), _p(zr), B, C, T, pitch, int(relu), _p(sums),
+                                               _stream()), "ts_bn_bwd_reduce")
+    return sums if partial else sums.sum(0, dtype=torch.float64)
 
 
 def bn_bwd_apply(dy, y, z, zr, coef, coef_r, T, relu=True) -> Tuple[Tensor, Optional[Tensor]]:
     B, C, pitch = z.shape
     dz = torch.empty_like(z)
     dzr = torch.empty_like(z) if zr is not None else None
-    _lib.check(_lib.lib().ts_bn_bwd_apply(_p(dy), _p(y), _p(z), _p(zr), _p(coef), _p(coef_r), B, C, T, pitch, int(relu),
-                                          _p(dz), _p(dzr), _stream()), "ts_bn_bwd_apply")
+    with ops._timed("bn_bwd_apply", bytes=B * C * T * 2 * (6 if zr is not None else 4), flops=0):
+        _lib.check(_lib.lib().ts_bn_bwd_apply(_p(dy), _p(y), _p(z), _p(zr), _p(coef), _p(coef_r), B, C, T, pitch,
+                                              int(relu), _p(dz), _p(dzr), _stream()), "ts_bn_bwd_apply")
     return dz, dzr
 
 
-def pw_wgrad(dz: Tensor, a: Tensor, T: int) -> Tensor:
-    """dW[co, ci] = sum_{b,t} dz[b,co,t] a[b,ci,t] (fp32)."""
+def pw_wgrad(dz: Tensor, a: Tensor, T: int, out: Optional[Tensor] = None) -> Tensor:
+    """dW[co, ci] = sum_{b,t} dz[b,co,t] a[b,ci,t] (fp32); written into ``out`` (any shape with Cout*Cin elements)."""
     B, Cout, pz = dz.shape
     Cin, pa = a.shape[1], a.shape[2]
     tiles = ((Cout + 127) // 128) * ((Cin + 255) // 256)
     nsplit = max(1, min(B, 148 // max(tiles, 1)))
-    part = torch.empty((nsplit, Cout, Cin), device=dz.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_pw_wgrad(_p(dz), pz, _p(a), pa, B, Cout, Cin, T, nsplit, _p(part), _stream()), "ts_pw_wgrad")
-    return part.sum(0)
+    if nsplit == 1 and out is not None and out.is_contiguous():
+        part = out.view(1, Cout, Cin)
+    else:
+        part = torch.empty((nsplit, Cout, Cin), device=dz.device, dtype=torch.float32)
+    with ops._timed("pw_wgrad", bytes=B * (Cout + Cin) * T * 2 + nsplit * Cout * Cin * 4, flops=2 * B * T * Cout * Cin):
+        _lib.check(_lib.lib().ts_pw_wgrad(_p(dz), pz, _p(a), pa, B, Cout, Cin, T, nsplit, _p(part), _stream()),
+                   "ts_pw_wgrad")
+    if out is None:
+        return part.sum(0)
+    if part.data_ptr() != out.data_ptr():
+        torch.sum(part, 0, out=out.view(Cout, Cin))
+    return out
 
 
-def dw_wgrad(da: Tensor, T_out: int, x: Tensor, T_in: int, lens_in: Optional[Tensor], K: int, S: int, D: int, P: int
-             ) -> Tensor:
+def dw_wgrad(da: Tensor, T_out: int, x: Tensor, T_in: int, lens_in: Optional[Tensor], K: int, S: int, D: int, P: int,
+             out: Optional[Tensor] = None) -> Tensor:
     B, C, po = da.shape
     pi = x.shape[2]
-    bchunk = max(1, min(B, (B + 7) // 8))   # ~8 batch slices per channel: C x 8 CTAs
+    bchunk = min(B, 8)   # utterances per CTA (8 rows amortise the staging / reduction phases; measured 2..32)
     nchunk = (B + bchunk - 1) // bchunk
     part = torch.empty((nchunk, C, K), device=da.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_dw_wgrad(_p(da), T_out, po, _p(x), T_in, pi, _p(lens_in), B, C, K, S, D, P, bchunk, _p(part),
-                                      _stream()), "ts_dw_wgrad")
-    return part.sum(0)
+    with ops._timed("dw_wgrad", bytes=B * C * (T_out + T_in) * 2, flops=2 * B * C * T_out * K):
+        _lib.check(_lib.lib().ts_dw_wgrad(_p(da), T_out, po, _p(x), T_in, pi, _p(lens_in), B, C, K, S, D, P, bchunk,
+                                          _p(part), _stream()), "ts_dw_wgrad")
+    if out is None:
+        return part.sum(0)
+    torch.sum(part, 0, out=out.view(C, K))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ block trainer
@@ -107,42 +177,13 @@ class _Sub:
     P: int
 
 
-def _bn_forward_stats(bn: nn.BatchNorm1d, st: Tensor, n: int, update_running: bool):
-    """batch mean / biased var from (sum, sumsq); returns (scale, shift, mean, inv) as f32 [C]; updates running stats like
-    nn.BatchNorm1d(momentum=0.1) does in train() (unbiased variance for the running estimate)."""
-    mean = st[:, 0] / n
-    var = torch.clamp(st[:, 1] / n - mean * mean, min=0.0)
-    inv = torch.rsqrt(var + bn.eps)
-    g = bn.weight.detach().double()
-    scale = g * inv
-    shift = bn.bias.detach().double() - mean * scale
-    if update_running and bn.track_running_stats:
-        with torch.no_grad():
-            m = bn.momentum if bn.momentum is not None else BN_MOMENTUM
-            bn.running_mean.mul_(1 - m).add_(m * mean.float())
-            bn.running_var.mul_(1 - m).add_(m * (var * n / max(n - 1, 1)).float())
-            bn.num_batches_tracked += 1
-    return scale.float().contiguous(), shift.float().contiguous(), mean, inv
-
-
-def _bn_backward_coef(bn: nn.BatchNorm1d, s0: Tensor, s1: Tensor, mean: Tensor, inv: Tensor, n: int):
-    """(dgamma, dbeta, coef[C,3]) with dz = coef0 * dym + coef1 * z + coef2."""
-    g = bn.weight.detach().double()
-    dbeta = s0
-    dgamma = inv * (s1 - mean * s0)
-    a = g * inv
-    b = -g * inv * inv * dgamma / n
-    c = -a * dbeta / n - b * mean
-    coef = torch.stack([a, b, c], dim=1).float().contiguous()
-    return dgamma.float(), dbeta.float(), coef
-
-
-def _accum(p: nn.Parameter, g: Tensor):
-    g = g.reshape(p.shape).to(p.dtype)
+def _grad(p: nn.Parameter) -> Tensor:
+    """The gradient buffer of `p` (created on first use).  Every parameter of the encoder receives exactly one contribution
+    per step, so the backward kernels WRITE into these buffers (no zeroing pass, no accumulation); CTCTrainStep points them
+    at slices of one flat buffer so that the all-reduce needs no packing."""
     if p.grad is None:
-        p.grad = g.clone()
-    else:
-        p.grad.add_(g)
+        p.grad = torch.zeros_like(p)
+    return p.grad
 
 
 def _bf16_taps(w: Tensor) -> Tensor:
@@ -204,13 +245,13 @@ class BlockTrainer:
             wpw = sb.pw.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
             z = ops.pw_gemm(wpw, a, None, None, Ta, None, None, False, False, None, None, None)
             nn_ = B * Ta
-            scale, shift, mean, inv = _bn_forward_stats(sb.bn, row_stats(z, Ta), nn_, update_running)
+            scale, shift, mean, inv = bn_finalize(row_stats_partial(z, Ta), nn_, sb.bn, update_running)
             rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, mean=mean, inv=inv, n=nn_, wpw=wpw)
             if last and self.res is not None:
                 rconv, rbn = self.res
                 wr = rconv.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
                 zr = ops.pw_gemm(wr, x, None, None, T, None, None, False, False, None, None, None)
-                scale_r, shift_r, mean_r, inv_r = _bn_forward_stats(rbn, row_stats(zr, T), B * T, update_running)
+                scale_r, shift_r, mean_r, inv_r = bn_finalize(row_stats_partial(zr, T), B * T, rbn, update_running)
                 y = bn_apply(z, scale, shift, zr, scale_r, shift_r, Ta, la if zero_tail else None, True)
                 rec.update(zr=zr, mean_r=mean_r, inv_r=inv_r, wr=wr)
             else:
@@ -219,6 +260,12 @@ class BlockTrainer:
             rec["y"] = y
             tape["subs"].append(rec)
             cur, Tc, lc = y, Ta, la
+        if update_running:
+            nbt = [sb.bn.num_batches_tracked for sb in self.subs if sb.bn.track_running_stats]
+            if self.res is not None and self.res[1].track_running_stats:
+                nbt.append(self.res[1].num_batches_tracked)
+            if nbt:
+                torch._foreach_add_(nbt, 1)
         return y, Tc, lc, tape
 
     # -- backward --------------------------------------------------------------------------------------
@@ -231,19 +278,15 @@ class BlockTrainer:
             last = r == n - 1
             has_res = last and self.res is not None
             Ta = rec["Ta"]
-            sums = bn_bwd_reduce(g, rec["y"], rec["z"], rec.get("zr") if has_res else None, Ta, True)
-            dgamma, dbeta, coef = _bn_backward_coef(sb.bn, sums[:, 0], sums[:, 1], rec["mean"], rec["inv"], rec["n"])
-            _accum(sb.bn.weight, dgamma)
-            _accum(sb.bn.bias, dbeta)
+            sums = bn_bwd_reduce(g, rec["y"], rec["z"], rec.get("zr") if has_res else None, Ta, True, partial=True)
+            coef = bn_bwd_coef(sums, 1, rec["n"], sb.bn, rec["mean"], rec["inv"])
             coef_r = None
             if has_res:
                 rconv, rbn = self.res
-                dgr, dbr, coef_r = _bn_backward_coef(rbn, sums[:, 0], sums[:, 2], rec["mean_r"], rec["inv_r"], rec["n"])
-                _accum(rbn.weight, dgr)
-                _accum(rbn.bias, dbr)
+                coef_r = bn_bwd_coef(sums, 2, rec["n"], rbn, rec["mean_r"], rec["inv_r"])
             dz, dzr = bn_bwd_apply(g, rec["y"], rec["z"], rec.get("zr") if has_res else None, coef, coef_r, Ta, True)
             # pointwise conv: weight gradient on the tensor cores, input gradient = W^T dz (masked like `a` was)
-            _accum(sb.pw.weight, pw_wgrad(dz, rec["a"], Ta))
+            pw_wgrad(dz, rec["a"], Ta, out=_grad(sb.pw.weight))
             first = r == 0
             need_da = sb.dw is not None or need_dx or not first
             da = None
@@ -251,7 +294,7 @@ class BlockTrainer:
                 wT = rec["wpw"].t().contiguous()
                 da = ops.pw_gemm(wT, dz, None, None, Ta, None, rec["la"], False, False, None, None, None)
             if sb.dw is not None:
-                _accum(sb.dw.weight, dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P))
+                dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight))
                 if (not first) or need_dx:
                     if sb.S != 1:
                         raise NotImplementedError("training step: input gradient of a strided depthwise conv")
@@ -263,7 +306,7 @@ class BlockTrainer:
                 g = da
             if has_res:
                 rconv, rbn = self.res
-                _accum(rconv.weight, pw_wgrad(dzr, tape["x"], tape["T"]))
+                pw_wgrad(dzr, tape["x"], tape["T"], out=_grad(rconv.weight))
                 if need_dx:
                     dx_res = dzr
         if need_dx and self.res is not None:
@@ -296,52 +339,106 @@ class EncoderTrainer:
             g = self.blocks[i].backward(tapes[i], g, need_dx=(i > 0))
 
 
-class CTCTrainStep:
-    """One optimisation step of a ``CTCModule`` (QuartzNet family): features (no grad) -> encoder (kernels) -> decoder +
-    CTC loss (torch autograd) -> encoder backward (kernels) -> gradient all-reduce (NCCL when initialised) -> AdamW."""
+class _StepGraph:
+    """One captured forward + loss + backward for fixed input shapes."""
 
-    def __init__(self, module, lr: float = 3e-4, blank_idx: Optional[int] = None, optimizer: Optional[torch.optim.Optimizer] = None):
+    def __init__(self, graph, audio, lengths, y, y_len, loss, kernels_per_replay):
+        self.graph, self.audio, self.lengths, self.y, self.y_len, self.loss = graph, audio, lengths, y, y_len, loss
+        self.kernels_per_replay = kernels_per_replay   # launches of this library's kernels captured in the graph
+        self.replays = 0
+
+
+class CTCTrainStep:
+    """One optimisation step of a ``CTCModule`` (QuartzNet family), mirroring ``BaseCTCModule.training_step`` +
+    ``configure_optimizers`` (src/thunder/module.py:102-127, :129-140): features (no grad) -> encoder forward (kernels) ->
+    decoder GEMM -> CTC loss kernel -> decoder / encoder backward (kernels) -> gradient all-reduce (NCCL when initialised)
+    -> AdamW (torch's fused multi-tensor kernel, as the reference uses torch.optim.AdamW).
+
+    All gradients live in ONE flat fp32 buffer (``param.grad`` are views): the all-reduce is a single in-place collective.
+    With ``use_graph`` the whole forward + loss + backward (~1400 launches for QuartzNet 15x5) is captured in a CUDA graph
+    per input shape and replayed; inputs are copied into the graph's static buffers."""
+
+    def __init__(self, module, lr: float = 3e-4, blank_idx: Optional[int] = None,
+                 optimizer: Optional[torch.optim.Optimizer] = None, use_graph: bool = True):
         self.m = module
         self.enc = EncoderTrainer(module.encoder)
         self.params = [p for p in list(module.encoder.parameters()) + list(module.decoder.parameters())]
-        self.opt = optimizer or torch.optim.AdamW(self.params, lr=lr)
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("CTCTrainStep runs on CUDA (sm_100a) modules only; there is no CPU fallback")
+        self.flat = flat_grad_views(self.params)
+        self.opt = optimizer or torch.optim.AdamW(self.params, lr=lr, capturable=True, fused=True)
         self.blank = blank_idx if blank_idx is not None else module.text_transform.vocab.blank_idx
+        self.use_graph = use_graph
+        self._graphs: Dict[tuple, _StepGraph] = {}
 
-    def loss_and_grads(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
+    # -- forward + loss + backward (all kernels of this library, no host synchronisation) ------------------------------
+    def _forward_backward(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor,
+                          update_running: bool = True) -> Tensor:
         m = self.m
-        for p in self.params:
-            p.grad = None
+        dec = m.decoder
+        V, Cd = dec.weight.shape[0], dec.weight.shape[1]
+        Vp = (V + 63) // 64 * 64
         with torch.no_grad():
             N = audio.shape[-1]
             hop = m.audio_transform[1].hop_length
             F = 1 + N // hop
             feats, feat_len = m.audio_transform.features(audio, lengths, bf16_pitch=ops.row_pitch(F))
-            l32 = feat_len.to(torch.int32)
-            rows, T, l32o, tapes = self.enc.forward(feats, F, l32)
-            enc_out = ops.unpack_rows(rows, T)                      # [B, C, T] f32 (layout change for torch autograd)
-        enc_out.requires_grad_(True)
-        logits = torch.nn.functional.conv1d(enc_out, m.decoder.weight, m.decoder.bias)
-        logprobs = torch.nn.functional.log_softmax(logits.permute(2, 0, 1), dim=2)
-        loss = torch.nn.functional.ctc_loss(logprobs, y, l32o.long(), y_lengths, blank=self.blank, reduction="mean",
-                                            zero_infinity=True)
-        loss.backward()
-        with torch.no_grad():
-            self.enc.backward(tapes, ops.pack_rows(enc_out.grad))
-        return loss.detach()
+            rows, T, l32o, tapes = self.enc.forward(feats, F, feat_len.to(torch.int32), update_running)
+            # decoder: logits = W_d enc + b (f32 rows), then CTC
+            wd = dec.weight.detach()[:, :, 0]
+            logits = ops.pw_gemm(wd.to(torch.bfloat16).contiguous(), rows, None, None, T, dec.bias.detach(), None, True,
+                                 False, None, None, None)
+            loss_b, dlogits = ctc_loss(logits, T, l32o, y, y_lengths.to(torch.int64), self.blank, Vp)
+            loss = loss_b.mean()
+            # decoder gradients: dW_d = dlogits enc^T, db = sum dlogits, d enc = W_d^T dlogits
+            dwd = pw_wgrad(dlogits, rows, T)
+            _grad(dec.weight).copy_(dwd[:V].view_as(dec.weight))
+            if dec.bias is not None:
+                _grad(dec.bias).copy_(row_stats_partial(dlogits, T).sum(0)[:V, 0])
+            wdT = torch.zeros((Cd, Vp), device=rows.device, dtype=torch.bfloat16)
+            wdT[:, :V] = wd.t()
+            d_enc = ops.pw_gemm(wdT, dlogits, None, None, T, None, None, False, False, None, None, None)
+            self.enc.backward(tapes, d_enc)
+        return loss
+
+    def _capture(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> _StepGraph:
+        sa, sl, sy, syl = audio.clone(), lengths.clone(), y.clone(), y_lengths.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):   # warm-up outside capture (lazy kernel attributes, allocator); leaves BN statistics alone
+                self._forward_backward(sa, sl, sy, syl, update_running=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            loss = self._forward_backward(sa, sl, sy, syl)
+        return _StepGraph(graph, sa, sl, sy, syl, loss, _lib.launch_count() - n0)
+
+    def loss_and_grads(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
+        """Mean CTC loss (device scalar); parameter gradients are left in ``param.grad``."""
+        if not self.use_graph:
+            return self._forward_backward(audio, lengths, y, y_lengths)
+        key = (tuple(audio.shape), tuple(y.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = self._capture(audio, lengths, y, y_lengths)
+        g.audio.copy_(audio, non_blocking=True)
+        g.lengths.copy_(lengths, non_blocking=True)
+        g.y.copy_(y, non_blocking=True)
+        g.y_len.copy_(y_lengths, non_blocking=True)
+        g.graph.replay()
+        g.replays += 1
+        return g.loss
+
+    def graph_launches(self) -> int:
+        """Kernel launches of this library executed through graph replays so far (ts_launch_count only sees eager ones)."""
+        return sum(g.kernels_per_replay * g.replays for g in self._graphs.values())
 
     def allreduce_grads(self) -> None:
-        import torch.distributed as dist
-
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in self.params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(dist.get_world_size())
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            p.grad.copy_(flat[off:off + k].view_as(p.grad))
-            off += k
+        allreduce_mean_(self.flat)
 
     def step(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
         loss = self.loss_and_grads(audio, lengths, y, y_lengths)
