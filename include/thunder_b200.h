@@ -162,12 +162,17 @@ int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, const void* z
 int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, const void* zr, const float* coef,
                     const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr, void* stream);
 /* pointwise-conv weight gradient dW[co, ci] = sum_{b,t} dz[b, co, t] a[b, ci, t] on the tensor cores;
- * part [nsplit, Cout, Cin] f32 partial sums over batch slices (the caller adds them) */
+ * part [nsplit, Cout, Cin] f32 partial sums over even shares of the B * ceil(T/64) reduction chunks */
 int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B, int Cout, int Cin, int T, int nsplit,
                 float* part, void* stream);
-/* depthwise weight gradient: part[chunk, c, k] = sum_{b in chunk, t'} da[b, c, t'] xm[b, c, t' S + k D - P] */
+/* out[i] = sum_s part[s, i] in ascending s (deterministic); n a multiple of 4, 16-byte aligned pointers */
+int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, float* out, void* stream);
+/* depthwise weight gradient: part[chunk, c, k] = sum_{b in chunk, t'} da[b, c, t'] xm[b, c, t' S + k D - P] with xm = x
+ * masked to len_in (MaskedConv1d).  flags & TS_DW_INPUT_PREMASKED: both row tensors are already zero beyond the utterance
+ * length and in the pad up to the pitch (true for every producer of this library); with stride 1, equal pitches and
+ * bchunk >= B (a single chunk) this selects the tensor-core kernel (dwwgrad_mma.cu). */
 int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
-                int B, int C, int K, int S, int D, int P, int bchunk, float* part, void* stream);
+                int B, int C, int K, int S, int D, int P, int bchunk, int flags, float* part, void* stream);
 
 /* BatchNorm train()-mode statistics from the per-utterance partial sums of ts_row_stats (part [NB, C, 2]):
  * mean, biased variance over n = B*T positions -> scale = gamma * inv, shift = beta - mean * scale, mean, inv = rsqrt(var +

@@ -351,3 +351,32 @@ def test_bn_finalize_and_bwd_coef_kernels():
         cc = -a * s3[:, 0] / n - bb * m
         assert rel_err(bn.weight.grad.cpu().numpy(), dg)[0] < 1e-5 and rel_err(bn.bias.grad.cpu().numpy(), s3[:, 0])[0] < 1e-6
         assert rel_err(coef, np.stack([a, bb, cc], 1))[0] < 1e-5
+
+
+@pytest.mark.parametrize("K,D,C,B,T", [(33, 1, 7, 5, 201), (39, 1, 3, 9, 751), (75, 1, 150, 3, 100), (87, 2, 5, 4, 333),
+                                        (5, 1, 4, 17, 64), (11, 1, 2, 2, 129), (127, 1, 3, 2, 300)])
+def test_dw_wgrad_tensor_core_kernel(K, D, C, B, T):
+    """dwwgrad_mma.cu (windows-as-K MMA + diagonal sums) against a float64 correlation of the same bf16 rows; ragged
+    lengths, batch not a multiple of the utterance group, halos of 1-2 windows, dilation 2."""
+    from thunder_speech_b200 import _lib
+    from thunder_speech_b200.train import dw_wgrad
+
+    rng = np.random.default_rng(K + C)
+    P = D * (K - 1) // 2
+    x = rng.standard_normal((B, C, T)).astype(np.float32)
+    da = rng.standard_normal((B, C, T)).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    lens[0] = T
+    l32 = torch.from_numpy(lens).cuda()
+    xr, dar = ops.pack_rows(torch.from_numpy(x).cuda(), l32), ops.pack_rows(torch.from_numpy(da).cuda(), l32)
+    n0 = _lib.launch_count()
+    got = dw_wgrad(dar, T, xr, T, l32, K, 1, D, P, premasked=True).cpu().numpy()
+    assert _lib.launch_count() == n0 + 1
+    xm = xr.float().cpu().numpy()[:, :, :T].astype(np.float64)
+    dd = dar.float().cpu().numpy()[:, :, :T].astype(np.float64)
+    xp = np.pad(xm, ((0, 0), (0, 0), (P, P)))
+    ref = np.stack([(dd * xp[:, :, k * D: k * D + T]).sum((0, 2)) for k in range(K)], axis=1)
+    assert rel_err(got, ref)[0] < 1e-4, (K, D, rel_err(got, ref))
+    # and the SIMT kernel on the same data agrees
+    simt = dw_wgrad(dar, T, xr, T, l32, K, 1, D, P, premasked=False).cpu().numpy()
+    assert rel_err(simt, ref)[0] < 1e-4

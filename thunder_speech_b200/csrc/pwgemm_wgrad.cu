@@ -4,9 +4,11 @@
 //
 // Both operands are activation rows [B, C, pitch] with time contiguous, i.e. BOTH are K-major for a GEMM whose
 // reduction dimension is (batch, time): A = dz tile [128 co x 64 t], B = a tile [BN ci x 64 t], SWIZZLE_128B boxes
-// straight from the 3-D tensor maps (frames >= T are zero-filled by TMA).  Grid = (Cout/128, Cin/BN, SPLIT): each CTA
-// reduces its slice of the batch into a TMEM accumulator and writes an fp32 partial [SPLIT, Cout, Cin]; the caller sums
-// the partials (deterministic, no atomics).  Same warp-specialised TMA / MMA / epilogue structure as pwgemm.cu.
+// straight from the 3-D tensor maps (frames >= T are zero-filled by TMA).  The reduction is cut into k-chunks of 64 frames
+// numbered over (utterance, time chunk); grid = (Cout/128, Cin/BN, SPLIT) and each CTA reduces an even share of the
+// k-chunks into a TMEM accumulator and writes an fp32 partial [SPLIT, Cout, Cin].  The output matrix is tiny next to the
+// reduction length (256x256 vs 24k frames), so SPLIT is chosen to fill all 148 SMs; ts_pw_wgrad_reduce then sums the
+// partials in a fixed order (deterministic, no atomics).  Same warp-specialised TMA / MMA / epilogue structure as pwgemm.cu.
 #include "ts_common.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
@@ -23,7 +25,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 struct Params {
   CUtensorMap a, b;   // dz rows (t, co, b) box (64, 128, 1);  a rows (t, ci, b) box (64, 256, 1)
   int Cout, Cin, T, B;
-  int bsplit;         // utterances per CTA
+  int nsplit;
   float* part;        // [SPLIT, Cout, Cin]
 };
 
@@ -38,9 +40,10 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, split = blockIdx.z;
-  const int b0 = split * p.bsplit, b1 = min(p.B, b0 + p.bsplit);
   const int tchunks = (p.T + BK - 1) / BK;
-  const int num_k = (b1 - b0) * tchunks;
+  const int total_k = p.B * tchunks;
+  const int k_begin = (int)((long long)total_k * split / p.nsplit);
+  const int num_k = (int)((long long)total_k * (split + 1) / p.nsplit) - k_begin;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.a);
@@ -69,7 +72,8 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
       ptx::mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
       uint8_t* sa = smem + s * STAGE_BYTES;
       ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-      const int b = b0 + kc / tchunks, t0 = (kc % tchunks) * BK;
+      const int kg = k_begin + kc;
+      const int b = kg / tchunks, t0 = (kg - b * tchunks) * BK;
       ptx::tma_load_3d(sa, &p.a, &full_bar[s], t0, m0, b);
       ptx::tma_load_3d(sa + A_BYTES, &p.b, &full_bar[s], t0, n0, b);
     }
@@ -110,9 +114,16 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
       if (m < p.Cout) {
+        if ((p.Cin & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < p.Cin) orow[n0 + c0 + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; j += 4)
+            if (n0 + c0 + j < p.Cin)
+              *reinterpret_cast<uint4*>(orow + n0 + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.Cin) orow[n0 + c0 + j] = __uint_as_float(v[j]);
+        }
       }
     }
     ptx::tc_fence_before();
@@ -124,6 +135,29 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
   }
 }
 
+// out[i] = sum_s part[s][i], s ascending (fixed order); n4 = elements / 4
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ part, int nsplit, long long n4, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 8 <= nsplit; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (long long)(s + u) * n4 + i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+  }
+  for (; s < nsplit; ++s) {
+    const float4 v = __ldg(part + (long long)s * n4 + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[i] = acc;
+}
+
 }  // namespace wg
 }  // namespace ts
 
@@ -132,7 +166,8 @@ using namespace ts;
 extern "C" int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B, int Cout, int Cin, int T,
                            int nsplit, float* part, void* stream) {
   TS_REQUIRE(dz && a && part, TS_ERR_INVALID, "ts_pw_wgrad: null pointer");
-  TS_REQUIRE(B > 0 && Cout > 0 && Cin > 0 && T > 0 && nsplit > 0 && nsplit <= B, TS_ERR_INVALID, "ts_pw_wgrad: bad sizes");
+  TS_REQUIRE(B > 0 && Cout > 0 && Cin > 0 && T > 0 && nsplit > 0, TS_ERR_INVALID, "ts_pw_wgrad: bad sizes");
+  TS_REQUIRE(nsplit <= B * ceil_div(T, wg::BK), TS_ERR_INVALID, "ts_pw_wgrad: more splits than 64-frame chunks");
   TS_REQUIRE(dz_pitch % 8 == 0 && a_pitch % 8 == 0 && dz_pitch >= T && a_pitch >= T, TS_ERR_INVALID,
              "ts_pw_wgrad: pitches must be multiples of 8 frames and >= T");
   wg::Params p;
@@ -145,7 +180,7 @@ extern "C" int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pi
                               1)) != TS_OK)
     return rc;
   p.Cout = Cout; p.Cin = Cin; p.T = T; p.B = B;
-  p.bsplit = ceil_div(B, nsplit);
+  p.nsplit = nsplit;
   p.part = part;
   static bool attr_set = false;
   if (!attr_set) {
@@ -155,5 +190,16 @@ extern "C" int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pi
   dim3 grid(ceil_div(Cout, wg::BM), ceil_div(Cin, wg::BN), nsplit);
   wg::pw_wgrad_kernel<<<grid, 256, wg::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   TS_LAUNCH_CHECK("pw_wgrad_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, float* out, void* stream) {
+  TS_REQUIRE(part && out, TS_ERR_INVALID, "ts_pw_wgrad_reduce: null pointer");
+  TS_REQUIRE(nsplit > 0 && n > 0 && n % 4 == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: n must be a positive multiple of 4");
+  TS_REQUIRE((((uintptr_t)part | (uintptr_t)out) & 15) == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: 16-byte alignment required");
+  const long long n4 = n / 4;
+  wg::wgrad_reduce_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(part), nsplit, n4, reinterpret_cast<float4*>(out));
+  TS_LAUNCH_CHECK("wgrad_reduce_kernel");
   return TS_OK;
 }

@@ -347,14 +347,23 @@ int launch_dw_wgrad_tiled(const __nv_bfloat16* da, int T_out, int pitch_out, con
                           const int32_t* len_in, int B, int C, int K, int D, int P, int bchunk, float* part,
                           cudaStream_t st);
 
+int launch_dw_wgrad_mma(const __nv_bfloat16* da, int pitch_out, const __nv_bfloat16* x, int pitch_in, int B, int C, int K,
+                        int D, int P, float* out, cudaStream_t st);
+
 extern "C" int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in,
-                           const int32_t* len_in, int B, int C, int K, int S, int D, int P, int bchunk, float* part,
-                           void* stream) {
+                           const int32_t* len_in, int B, int C, int K, int S, int D, int P, int bchunk, int flags,
+                           float* part, void* stream) {
   TS_REQUIRE(da && x && part, TS_ERR_INVALID, "ts_dw_wgrad: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && K > 0 && K <= 256 && S > 0 && D > 0 && P >= 0 && bchunk > 0, TS_ERR_INVALID,
              "ts_dw_wgrad: bad sizes (K <= 256)");
   TS_REQUIRE(pitch_in % 8 == 0 && pitch_out % 8 == 0 && pitch_in >= T_in && pitch_out >= T_out, TS_ERR_INVALID,
              "ts_dw_wgrad: pitches must be multiples of 8 frames and >= T");
+  if (S == 1 && T_in == T_out && bchunk >= B && (flags & TS_DW_INPUT_PREMASKED) && option_dw_mma()) {
+    // tensor-core kernel (dwwgrad_mma.cu): whole batch per channel, writes part[0] = the final gradient
+    const int rc = launch_dw_wgrad_mma((const __nv_bfloat16*)da, pitch_out, (const __nv_bfloat16*)x, pitch_in, B, C, K, D, P,
+                                       part, (cudaStream_t)stream);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   if (S == 1) {   // register-tiled kernel (dwwgrad.cu); the kernel below is the generic fallback (strided stem)
     const int rc = launch_dw_wgrad_tiled((const __nv_bfloat16*)da, T_out, pitch_out, (const __nv_bfloat16*)x, T_in, pitch_in,
                                          len_in, B, C, K, D, P, bchunk, part, (cudaStream_t)stream);

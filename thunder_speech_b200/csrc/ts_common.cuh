@@ -17,6 +17,7 @@ void count_launch(int n = 1);
 int option_pw_big();  // 1: bf16-row GEMMs with Cout > 128 use the persistent 256x256-tile kernel (pwgemm2.cu)
 int option_dw_tma();  // 1: pre-masked stride-1 depthwise convs use the TMA Toeplitz kernel (dwmma2.cu)
 int option_dw_mma();  // 1: stride-1 depthwise convs run on the tensor cores (dwmma.cu), 0: SIMT kernels only
+int option_pw_bn();   // experiment switch (see api.cu)
 
 #define TS_REQUIRE(cond, code, ...)            \
   do {                                         \

@@ -134,7 +134,7 @@ def pw_wgrad(dz: Tensor, a: Tensor, T: int, out: Optional[Tensor] = None) -> Ten
     B, Cout, pz = dz.shape
     Cin, pa = a.shape[1], a.shape[2]
     tiles = ((Cout + 127) // 128) * ((Cin + 255) // 256)
-    nsplit = max(1, min(B, 148 // max(tiles, 1)))
+    nsplit = max(1, min(B * ((T + 63) // 64), 148 // max(tiles, 1)))   # fill the 148 SMs
     if nsplit == 1 and out is not None and out.is_contiguous():
         part = out.view(1, Cout, Cin)
     else:
@@ -143,25 +143,37 @@ def pw_wgrad(dz: Tensor, a: Tensor, T: int, out: Optional[Tensor] = None) -> Ten
         _lib.check(_lib.lib().ts_pw_wgrad(_p(dz), pz, _p(a), pa, B, Cout, Cin, T, nsplit, _p(part), _stream()),
                    "ts_pw_wgrad")
     if out is None:
-        return part.sum(0)
+        out = torch.empty((Cout, Cin), device=dz.device, dtype=torch.float32)
     if part.data_ptr() != out.data_ptr():
-        torch.sum(part, 0, out=out.view(Cout, Cin))
+        n = Cout * Cin
+        if n % 4 == 0 and out.is_contiguous() and out.data_ptr() % 16 == 0:
+            _lib.check(_lib.lib().ts_pw_wgrad_reduce(_p(part), nsplit, n, _p(out), _stream()), "ts_pw_wgrad_reduce")
+        else:
+            torch.sum(part, 0, out=out.view(Cout, Cin))
     return out
 
 
 def dw_wgrad(da: Tensor, T_out: int, x: Tensor, T_in: int, lens_in: Optional[Tensor], K: int, S: int, D: int, P: int,
-             out: Optional[Tensor] = None) -> Tensor:
+             out: Optional[Tensor] = None, premasked: bool = False) -> Tensor:
+    """dw[c, k] = sum_{b,t} da[b,c,t] x[b,c,t*S + k*D - P] (x masked to lens_in).  ``premasked``: both row tensors are
+    already zero beyond the utterance lengths and in the pitch pad -> stride-1 layers run on the tensor cores."""
     B, C, po = da.shape
     pi = x.shape[2]
-    bchunk = min(B, 8)   # utterances per CTA (8 rows amortise the staging / reduction phases; measured 2..32)
+    mma = premasked and S == 1 and T_in == T_out and pi == po and K <= 128
+    bchunk = B if mma else min(B, 8)   # SIMT kernels: 8 utterances per CTA amortise the staging / reduction phases
     nchunk = (B + bchunk - 1) // bchunk
-    part = torch.empty((nchunk, C, K), device=da.device, dtype=torch.float32)
+    if nchunk == 1 and out is not None and out.is_contiguous():
+        part = out.view(1, C, K)
+    else:
+        part = torch.empty((nchunk, C, K), device=da.device, dtype=torch.float32)
     with ops._timed("dw_wgrad", bytes=B * C * (T_out + T_in) * 2, flops=2 * B * C * T_out * K):
         _lib.check(_lib.lib().ts_dw_wgrad(_p(da), T_out, po, _p(x), T_in, pi, _p(lens_in), B, C, K, S, D, P, bchunk,
-                                          _p(part), _stream()), "ts_dw_wgrad")
+                                          _lib.TS_DW_INPUT_PREMASKED if premasked else 0, _p(part), _stream()),
+                   "ts_dw_wgrad")
     if out is None:
         return part.sum(0)
-    torch.sum(part, 0, out=out.view(C, K))
+    if part.data_ptr() != out.data_ptr():
+        torch.sum(part, 0, out=out.view(C, K))
     return out
 
 
@@ -294,7 +306,8 @@ class BlockTrainer:
                 wT = rec["wpw"].t().contiguous()
                 da = ops.pw_gemm(wT, dz, None, None, Ta, None, rec["la"], False, False, None, None, None)
             if sb.dw is not None:
-                dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight))
+                dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight),
+                         premasked=True)
                 if (not first) or need_dx:
                     if sb.S != 1:
                         raise NotImplementedError("training step: input gradient of a strided depthwise conv")
