@@ -174,6 +174,12 @@ int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, float* out, v
 int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
                 int B, int C, int K, int S, int D, int P, int bchunk, int flags, float* part, void* stream);
 
+/* Prepares every weight operand of a training step from the fp32 master weights in ONE launch.  `table` is a device array
+ * of n_entries rows of 8 int64: {src, dst, dstT, rows, cols, ldT, kind, first_tile}; tiles are 32 x 32 elements and
+ * first_tile is the running sum of ceil(rows/32) * ceil(cols/32).  kind 0 (pointwise / decoder weight [rows, cols] f32):
+ * dst = bf16 copy, dstT = bf16 transpose with leading dimension ldT.  kind 1 (depthwise taps [rows, cols] f32): dst = the
+ * taps rounded to bf16 (stored f32), dstT = the same flipped along cols (the taps of the input-gradient convolution). */
+int ts_prep_weights(const long long* table, int n_entries, long long total_tiles, void* stream);
 /* BatchNorm train()-mode statistics from the per-utterance partial sums of ts_row_stats (part [NB, C, 2]):
  * mean, biased variance over n = B*T positions -> scale = gamma * inv, shift = beta - mean * scale, mean, inv = rsqrt(var +
  * eps); running_mean / running_var (nullable) are updated in place with `momentum` and the UNBIASED variance, as

@@ -135,27 +135,42 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
   }
 }
 
-// out[i] = sum_s part[s][i], s ascending (fixed order); n4 = elements / 4
+// out[i] = sum_s part[s][i] in a fixed order; n4 = elements / 4.  A block owns 32 float4 columns; its 8 warps each sum a
+// contiguous slice of the splits (all loads independent), then warp 0 adds the 8 slice sums in ascending order.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ part, int nsplit, long long n4, float4* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
+  __shared__ float4 sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  const int per = (nsplit + 7) >> 3;
+  const int s0 = w * per, s1 = min(nsplit, s0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int s = 0;
-  for (; s + 8 <= nsplit; s += 8) {
-    float4 v[8];
+  if (i < n4) {
+    int s = s0;
+    for (; s + 4 <= s1; s += 4) {
+      float4 v[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (long long)(s + u) * n4 + i);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(part + (long long)(s + u) * n4 + i);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      for (int u = 0; u < 4; ++u) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+    for (; s < s1; ++s) {
+      const float4 v = __ldg(part + (long long)s * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  for (; s < nsplit; ++s) {
-    const float4 v = __ldg(part + (long long)s * n4 + i);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  sm[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && i < n4) {
+    float4 t = sm[0][lane];
+#pragma unroll
+    for (int u = 1; u < 8; ++u) {
+      t.x += sm[u][lane].x; t.y += sm[u][lane].y; t.z += sm[u][lane].z; t.w += sm[u][lane].w;
+    }
+    out[i] = t;
   }
-  out[i] = acc;
 }
 
 }  // namespace wg
@@ -198,7 +213,7 @@ extern "C" int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, fl
   TS_REQUIRE(nsplit > 0 && n > 0 && n % 4 == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: n must be a positive multiple of 4");
   TS_REQUIRE((((uintptr_t)part | (uintptr_t)out) & 15) == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: 16-byte alignment required");
   const long long n4 = n / 4;
-  wg::wgrad_reduce_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+  wg::wgrad_reduce_kernel<<<(unsigned)ceil_div64(n4, 32), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(part), nsplit, n4, reinterpret_cast<float4*>(out));
   TS_LAUNCH_CHECK("wgrad_reduce_kernel");
   return TS_OK;

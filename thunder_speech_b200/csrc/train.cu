@@ -266,18 +266,25 @@ extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, con
 namespace ts {
 namespace train {
 
+// One warp per channel: lanes stride over the NB partials (independent loads), shuffle-reduce in double.
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int NB, int C, double n, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ inv_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < NB; ++b) {
+  for (int b = lane; b < NB; b += 32) {
     const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)b * C + c) * 2);
     s0 += v.x;
     s1 += v.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (lane != 0) return;
   const double mean = s0 / n;
   double var = s1 / n - mean * mean;
   var = var > 0.0 ? var : 0.0;
@@ -297,14 +304,20 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ part, int NB, int C
                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                    const float* __restrict__ inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                    float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < NB; ++b) {
+  for (int b = lane; b < NB; b += 32) {
     const float* p = part + ((size_t)b * C + c) * 3;
     s0 += p[0];
     s1 += p[which];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (lane != 0) return;
   const double m = mean[c], iv = inv[c], g = gamma[c];
   const double dg = iv * (s1 - m * s0);
   const double a = g * iv;
@@ -326,7 +339,7 @@ extern "C" int ts_bn_finalize(const float* part, int NB, int C, double n, const 
   TS_REQUIRE(part && gamma && beta && scale && shift && mean && inv, TS_ERR_INVALID, "ts_bn_finalize: null pointer");
   TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID,
              "ts_bn_finalize: bad sizes");
-  train::bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(part, NB, C, n, gamma, beta, eps, momentum,
+  train::bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, C, n, gamma, beta, eps, momentum,
                                                                                running_mean, running_var, scale, shift,
                                                                                mean, inv);
   TS_LAUNCH_CHECK("bn_finalize_kernel");
@@ -337,9 +350,78 @@ extern "C" int ts_bn_bwd_coef(const float* part, int NB, int C, int which, doubl
                               const float* inv, float* dgamma, float* dbeta, float* coef, void* stream) {
   TS_REQUIRE(part && gamma && mean && inv && dgamma && dbeta && coef, TS_ERR_INVALID, "ts_bn_bwd_coef: null pointer");
   TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (which == 1 || which == 2), TS_ERR_INVALID, "ts_bn_bwd_coef: bad arguments");
-  train::bn_bwd_coef_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(part, NB, C, which, n, gamma, mean, inv,
+  train::bn_bwd_coef_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, C, which, n, gamma, mean, inv,
                                                                                dgamma, dbeta, coef);
   TS_LAUNCH_CHECK("bn_bwd_coef_kernel");
+  return TS_OK;
+}
+
+namespace ts {
+namespace train {
+
+// One launch prepares every weight operand of a training step from the fp32 master weights.  Table row (8 x int64):
+//   src, dst, dstT, rows, cols, ldT, kind, first_tile
+// kind 0 (pointwise / decoder weight [rows, cols] f32): dst = bf16 copy [rows, cols], dstT = bf16 transpose [cols, ldT]
+// kind 1 (depthwise taps [rows, cols] f32): dst = taps rounded to bf16 kept as f32, dstT = the same, flipped along cols
+// Tiles are 32 x 32; a CTA finds its table row by binary search over first_tile.
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const long long* __restrict__ tab, int n) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const long long* e = tab + lo * 8;
+  const float* src = reinterpret_cast<const float*>(e[0]);
+  const int rows = (int)e[3], cols = (int)e[4], ldT = (int)e[5], kind = (int)e[6];
+  const int t = (int)((long long)blockIdx.x - e[7]);
+  const int tc = (cols + 31) >> 5;
+  const int r0 = (t / tc) << 5, c0 = (t % tc) << 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (kind == 0) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e[1]);
+    __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(e[2]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      float v = 0.f;
+      if (r < rows && c < cols) {
+        v = src[(size_t)r * cols + c];
+        dst[(size_t)r * cols + c] = __float2bfloat16(v);
+      }
+      tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, r = r0 + tx;
+      if (r < rows && c < cols) dstT[(size_t)c * ldT + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(e[1]);
+    float* dstF = reinterpret_cast<float*>(e[2]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      if (r < rows && c < cols) {
+        const float v = __bfloat162float(__float2bfloat16(src[(size_t)r * cols + c]));
+        dst[(size_t)r * cols + c] = v;
+        dstF[(size_t)r * cols + (cols - 1 - c)] = v;
+      }
+    }
+  }
+}
+
+}  // namespace train
+}  // namespace ts
+
+extern "C" int ts_prep_weights(const long long* table, int n_entries, long long total_tiles, void* stream) {
+  TS_REQUIRE(table != nullptr && n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), TS_ERR_INVALID,
+             "ts_prep_weights: bad arguments");
+  train::prep_weights_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(table, n_entries);
+  TS_LAUNCH_CHECK("prep_weights_kernel");
   return TS_OK;
 }
 

@@ -198,10 +198,52 @@ def _grad(p: nn.Parameter) -> Tensor:
     return p.grad
 
 
-def _bf16_taps(w: Tensor) -> Tensor:
-    """Depthwise taps [C, K] as the training step computes with them: rounded to bf16 (the Toeplitz tensor-core path
-    holds its taps in bf16; the SIMT paths get the same rounded values so every layer sees one set of weights)."""
-    return w.detach()[:, 0, :].to(torch.bfloat16).float().contiguous()
+class WeightPack:
+    """The compute-precision copies of the fp32 master weights, rebuilt by ONE kernel launch per step (ts_prep_weights):
+
+      pointwise / decoder weight [Cout, Cin, 1]  ->  bf16 ``w`` [Cout, Cin] (forward GEMM) and bf16 ``wT`` [Cin, ld]
+                                                     (input-gradient GEMM; ld = Cout rounded up to 64 for the decoder)
+      depthwise taps [C, 1, K]                   ->  f32 ``w`` [C, K] rounded to bf16 (the Toeplitz tensor-core path holds
+                                                     its taps in bf16; every path sees the same values) and ``wT`` = the
+                                                     taps flipped along K (the input-gradient convolution)
+
+    The buffers and the device-side table are allocated once; parameters are updated in place by the optimiser, so the
+    table stays valid."""
+
+    def __init__(self, entries: List[Tuple[str, nn.Parameter]]):
+        self.views: Dict[int, Tuple[Tensor, Tensor]] = {}
+        rows_tab = []
+        tiles = 0
+        self._keep = []
+        for kind, p in entries:
+            dev = p.device
+            if kind == "pw":
+                rows, cols = p.shape[0], p.shape[1]
+                # K of the input-gradient GEMM = channels of the dz rows; only a row pitch that is not 16-byte aligned
+                # (the decoder's V = 29) is padded, and then the gradient rows are padded to the same count
+                ld = rows if rows % 8 == 0 else (rows + 63) // 64 * 64
+                w = torch.empty((rows, cols), device=dev, dtype=torch.bfloat16)
+                wT = torch.zeros((cols, ld), device=dev, dtype=torch.bfloat16)
+                k = 0
+            else:
+                rows, cols = p.shape[0], p.shape[2]
+                ld = cols
+                w = torch.empty((rows, cols), device=dev, dtype=torch.float32)
+                wT = torch.empty((rows, cols), device=dev, dtype=torch.float32)
+                k = 1
+            if not p.is_contiguous():
+                raise ValueError("WeightPack: parameters must be contiguous")
+            rows_tab.append([p.data_ptr(), w.data_ptr(), wT.data_ptr(), rows, cols, ld, k, tiles])
+            tiles += ((rows + 31) // 32) * ((cols + 31) // 32)
+            self.views[id(p)] = (w, wT)
+        self.n, self.tiles = len(rows_tab), tiles
+        self.table = torch.tensor(rows_tab, dtype=torch.int64).to(entries[0][1].device)
+
+    def refresh(self) -> None:
+        _lib.check(_lib.lib().ts_prep_weights(_p(self.table), self.n, self.tiles, _stream()), "ts_prep_weights")
+
+    def get(self, p: nn.Parameter) -> Tuple[Tensor, Tensor]:
+        return self.views[id(p)]
 
 
 class BlockTrainer:
@@ -236,9 +278,25 @@ class BlockTrainer:
             if rl[0].stride != 1:
                 raise NotImplementedError("training step: strided residual branches are not implemented yet")
             self.res = (rl[0].conv, rl[1].layer[0])
+        self.pack: Optional[WeightPack] = None      # set by EncoderTrainer (one pack for the whole model)
+        self._own_pack = False
+
+    def pack_entries(self) -> List[Tuple[str, nn.Parameter]]:
+        ent = []
+        for sb in self.subs:
+            if sb.dw is not None:
+                ent.append(("dw", sb.dw.weight))
+            ent.append(("pw", sb.pw.weight))
+        if self.res is not None:
+            ent.append(("pw", self.res[0].weight))
+        return ent
 
     # -- forward ---------------------------------------------------------------------------------------
     def forward(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool, update_running: bool = True):
+        if self.pack is None:            # stand-alone use (block-level tests): own pack, refreshed every forward
+            self.pack, self._own_pack = WeightPack(self.pack_entries()), True
+        if self._own_pack:
+            self.pack.refresh()
         tape = dict(x=x, T=T, lens=lens, subs=[])
         cur, Tc, lc = x, T, lens
         B = x.shape[0]
@@ -247,21 +305,20 @@ class BlockTrainer:
         for r, sb in enumerate(self.subs):
             last = r == n - 1
             if sb.dw is not None:
-                w = _bf16_taps(sb.dw.weight)
-                a = ops.dw_conv(cur, Tc, w, sb.S, sb.D, sb.P, lc, True)
+                a = ops.dw_conv(cur, Tc, self.pack.get(sb.dw.weight)[0], sb.S, sb.D, sb.P, lc, True)
                 Ta = conv_out_length(Tc, sb.K, sb.S, sb.P, sb.D)
                 la = lc if (lc is None or (sb.S == 1 and 2 * sb.P == sb.D * (sb.K - 1))) else ops.conv_lengths(
                     lc, sb.K, sb.S, sb.D, sb.P)
             else:
                 a, Ta, la = cur, Tc, lc
-            wpw = sb.pw.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
+            wpw = self.pack.get(sb.pw.weight)[0]
             z = ops.pw_gemm(wpw, a, None, None, Ta, None, None, False, False, None, None, None)
             nn_ = B * Ta
             scale, shift, mean, inv = bn_finalize(row_stats_partial(z, Ta), nn_, sb.bn, update_running)
             rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, mean=mean, inv=inv, n=nn_, wpw=wpw)
             if last and self.res is not None:
                 rconv, rbn = self.res
-                wr = rconv.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
+                wr = self.pack.get(rconv.weight)[0]
                 zr = ops.pw_gemm(wr, x, None, None, T, None, None, False, False, None, None, None)
                 scale_r, shift_r, mean_r, inv_r = bn_finalize(row_stats_partial(zr, T), B * T, rbn, update_running)
                 y = bn_apply(z, scale, shift, zr, scale_r, shift_r, Ta, la if zero_tail else None, True)
@@ -303,7 +360,7 @@ class BlockTrainer:
             need_da = sb.dw is not None or need_dx or not first
             da = None
             if need_da:
-                wT = rec["wpw"].t().contiguous()
+                wT = self.pack.get(sb.pw.weight)[1]
                 da = ops.pw_gemm(wT, dz, None, None, Ta, None, rec["la"], False, False, None, None, None)
             if sb.dw is not None:
                 dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight),
@@ -311,7 +368,7 @@ class BlockTrainer:
                 if (not first) or need_dx:
                     if sb.S != 1:
                         raise NotImplementedError("training step: input gradient of a strided depthwise conv")
-                    wflip = _bf16_taps(sb.dw.weight).flip(-1).contiguous()
+                    wflip = self.pack.get(sb.dw.weight)[1]
                     g = ops.dw_conv(da, Ta, wflip, 1, sb.D, sb.D * (sb.K - 1) - sb.P, rec["lin"], True)
                 else:
                     g = None
@@ -325,7 +382,7 @@ class BlockTrainer:
         if need_dx and self.res is not None:
             # dx = dx_main + W_r^T dz_r, masked by the block-input lengths (epilogue: acc + 1 * y1)
             rconv, _ = self.res
-            wrT = tape["subs"][-1]["wr"].t().contiguous()
+            wrT = self.pack.get(rconv.weight)[1]
             ones = torch.ones((g.shape[0], wrT.shape[0]), device=g.device, dtype=torch.float32)
             g = ops.pw_gemm(wrT, dx_res, None, None, tape["T"], None, tape["lens"], False, False, None, ones, g)
         return g if need_dx else None
@@ -337,8 +394,20 @@ class EncoderTrainer:
     def __init__(self, encoder: nn.Module):
         self.encoder = encoder
         self.blocks = [BlockTrainer(b) for b in encoder.children()]
+        self.extra_entries: List[Tuple[str, nn.Parameter]] = []   # e.g. the decoder weight (CTCTrainStep)
+        self.pack: Optional[WeightPack] = None
+
+    def build_pack(self) -> WeightPack:
+        ent = [e for bt in self.blocks for e in bt.pack_entries()] + self.extra_entries
+        self.pack = WeightPack(ent)
+        for bt in self.blocks:
+            bt.pack, bt._own_pack = self.pack, False
+        return self.pack
 
     def forward(self, rows: Tensor, T: int, lens: Optional[Tensor], update_running: bool = True):
+        if self.pack is None:
+            self.build_pack()
+        self.pack.refresh()
         tapes = []
         for i, bt in enumerate(self.blocks):
             rows, T, lens, tape = bt.forward(rows, T, lens, zero_tail=(i != len(self.blocks) - 1),
@@ -375,6 +444,7 @@ class CTCTrainStep:
                  optimizer: Optional[torch.optim.Optimizer] = None, use_graph: bool = True):
         self.m = module
         self.enc = EncoderTrainer(module.encoder)
+        self.enc.extra_entries.append(("pw", module.decoder.weight))
         self.params = [p for p in list(module.encoder.parameters()) + list(module.decoder.parameters())]
         dev = self.params[0].device
         if dev.type != "cuda":
@@ -390,8 +460,8 @@ class CTCTrainStep:
                           update_running: bool = True) -> Tensor:
         m = self.m
         dec = m.decoder
-        V, Cd = dec.weight.shape[0], dec.weight.shape[1]
-        Vp = (V + 63) // 64 * 64
+        V = dec.weight.shape[0]
+        Vp = V if V % 8 == 0 else (V + 63) // 64 * 64    # = WeightPack's leading dimension of the transposed weight
         with torch.no_grad():
             N = audio.shape[-1]
             hop = m.audio_transform[1].hop_length
@@ -399,9 +469,8 @@ class CTCTrainStep:
             feats, feat_len = m.audio_transform.features(audio, lengths, bf16_pitch=ops.row_pitch(F))
             rows, T, l32o, tapes = self.enc.forward(feats, F, feat_len.to(torch.int32), update_running)
             # decoder: logits = W_d enc + b (f32 rows), then CTC
-            wd = dec.weight.detach()[:, :, 0]
-            logits = ops.pw_gemm(wd.to(torch.bfloat16).contiguous(), rows, None, None, T, dec.bias.detach(), None, True,
-                                 False, None, None, None)
+            wd, wdT = self.enc.pack.get(dec.weight)     # bf16 [V, Cd] and its transpose padded to [Cd, Vp]
+            logits = ops.pw_gemm(wd, rows, None, None, T, dec.bias.detach(), None, True, False, None, None, None)
             loss_b, dlogits = ctc_loss(logits, T, l32o, y, y_lengths.to(torch.int64), self.blank, Vp)
             loss = loss_b.mean()
             # decoder gradients: dW_d = dlogits enc^T, db = sum dlogits, d enc = W_d^T dlogits
@@ -409,8 +478,6 @@ class CTCTrainStep:
             _grad(dec.weight).copy_(dwd[:V].view_as(dec.weight))
             if dec.bias is not None:
                 _grad(dec.bias).copy_(row_stats_partial(dlogits, T).sum(0)[:V, 0])
-            wdT = torch.zeros((Cd, Vp), device=rows.device, dtype=torch.bfloat16)
-            wdT[:, :V] = wd.t()
             d_enc = ops.pw_gemm(wdT, dlogits, None, None, T, None, None, False, False, None, None, None)
             self.enc.backward(tapes, d_enc)
         return loss
