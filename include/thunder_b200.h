@@ -155,12 +155,18 @@ int ts_row_stats(const void* z, int B, int C, int T, int pitch, float* stats, vo
 int ts_bn_apply(const void* z, const float* scale, const float* shift, const void* zr, const float* scale_r,
                 const float* shift_r, int B, int C, int T, int pitch, const int32_t* lens, int relu, void* y,
                 void* stream);
-/* sums[b, c] = (sum dym, sum dym*z, sum dym*zr) with dym = dy * (y > 0) when relu: the reductions of BatchNorm backward */
+/* sums[b, c] = (sum dym, sum dym*z, sum dym*zr) with dym = dy * (y > 0) when relu: the reductions of BatchNorm backward.
+ * y may be NULL when relu: the mask is then rebuilt from z (and zr) with the forward scale / shift vectors exactly as
+ * ts_bn_apply evaluated it (saves reading y); mask_* are ignored otherwise */
 int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, const void* zr, int B, int C, int T, int pitch,
-                     int relu, float* sums, void* stream);
-/* dz = coef[c,0] dym + coef[c,1] z + coef[c,2]  (and the same for the residual branch): BatchNorm + ReLU backward */
+                     int relu, float* sums, const float* mask_scale, const float* mask_shift, const float* mask_scale_r,
+                     const float* mask_shift_r, void* stream);
+/* dz = coef[c,0] dym + coef[c,1] z + coef[c,2]  (and the same for the residual branch): BatchNorm + ReLU backward;
+ * y / mask_* as in ts_bn_bwd_reduce */
 int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, const void* zr, const float* coef,
-                    const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr, void* stream);
+                    const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr,
+                    const float* mask_scale, const float* mask_shift, const float* mask_scale_r,
+                    const float* mask_shift_r, void* stream);
 /* pointwise-conv weight gradient dW[co, ci] = sum_{b,t} dz[b, co, t] a[b, ci, t] on the tensor cores;
  * part [nsplit, Cout, Cin] f32 partial sums over even shares of the B * ceil(T/64) reduction chunks */
 int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pitch, int B, int Cout, int Cin, int T, int nsplit,
@@ -180,11 +186,18 @@ int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_i
  * dst = bf16 copy, dstT = bf16 transpose with leading dimension ldT.  kind 1 (depthwise taps [rows, cols] f32): dst = the
  * taps rounded to bf16 (stored f32), dstT = the same flipped along cols (the taps of the input-gradient convolution). */
 int ts_prep_weights(const long long* table, int n_entries, long long total_tiles, void* stream);
-/* BatchNorm train()-mode statistics from the per-utterance partial sums of ts_row_stats (part [NB, C, 2]):
+/* Training forward of a pointwise conv: out = W x as bf16 rows (no shift / activation / mask: x is zero beyond the
+ * utterance lengths) on the CTA-pair tcgen05 kernel, with the BatchNorm partial sums of the STORED values produced by
+ * the epilogue: stats [B, Cout, slots, 2] = (sum, sum of squares) per 128-frame block, slots = 2 * ceil(out_pitch / 256);
+ * every slot is written exactly once (deterministic).  TS_ERR_UNSUPPORTED when Cout <= 128 (use ts_pw_gemm +
+ * ts_row_stats). */
+int ts_pw_gemm_stats(const void* w, const void* x, int cin, int x_pitch, int B, int Cout, int T, void* out, int out_pitch,
+                     float* stats, int slots, void* stream);
+/* BatchNorm train()-mode statistics from partial sums part [NB, C, slots, 2] (ts_row_stats: slots = 1, NB = B):
  * mean, biased variance over n = B*T positions -> scale = gamma * inv, shift = beta - mean * scale, mean, inv = rsqrt(var +
  * eps); running_mean / running_var (nullable) are updated in place with `momentum` and the UNBIASED variance, as
  * nn.BatchNorm1d does (quartznet/blocks.py:222-228).  Everything on the device: no host round trip, graph-capturable. */
-int ts_bn_finalize(const float* part, int NB, int C, double n, const float* gamma, const float* beta, float eps,
+int ts_bn_finalize(const float* part, int NB, int slots, int C, double n, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
                    float* inv, void* stream);
 /* BatchNorm backward coefficients from the partial sums of ts_bn_bwd_reduce (part [NB, C, 3]; `which` = 1 for the main

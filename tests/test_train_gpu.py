@@ -316,6 +316,25 @@ def test_ctc_loss_kernel_vs_torch(B, V, T, Lmax, seed):
         assert loss[2].item() == 0.0 and np.all(g[2] == 0)
 
 
+def test_pw_gemm_stats_epilogue():
+    """Statistics from the GEMM epilogue == statistics of the stored bf16 output, for a time length with a partial tile."""
+    from thunder_speech_b200.train import pw_gemm_stats
+
+    rng = np.random.default_rng(11)
+    B, Cin, Cout, T = 5, 256, 384, 751
+    w = torch.from_numpy((rng.standard_normal((Cout, Cin)) / 16).astype(np.float32)).cuda().to(torch.bfloat16)
+    lens = torch.from_numpy(np.array([751, 700, 512, 300, 64], np.int32)).cuda()
+    x = ops.pack_rows(torch.from_numpy(rng.standard_normal((B, Cin, T)).astype(np.float32)).cuda(), lens)
+    z, st = pw_gemm_stats(w, x, T)
+    assert st.shape == (B, Cout, 6, 2)
+    zref = ops.pw_gemm(w, x, None, None, T, None, None, False, False, None, None, None)
+    assert torch.equal(z, zref)
+    zf = z.float()[:, :, :T].double()
+    got = st.double().sum(2).cpu().numpy()
+    assert rel_err(got[..., 0], zf.sum(-1).cpu().numpy())[0] < 1e-5
+    assert rel_err(got[..., 1], (zf * zf).sum(-1).cpu().numpy())[0] < 1e-5
+
+
 def test_bn_finalize_and_bwd_coef_kernels():
     from thunder_speech_b200.train import bn_bwd_coef, bn_finalize
 

@@ -48,15 +48,17 @@ SIGNATURES = {
     "ts_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_void_p]),
     "ts_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                 c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_int, c_void_p, c_void_p, c_void_p]),
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_pw_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ts_pw_wgrad_reduce": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "ts_dw_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_void_p, c_void_p]),
     "ts_prep_weights": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
-    "ts_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+    "ts_pw_gemm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                 c_void_p]),
+    "ts_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_bn_bwd_coef": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),

@@ -228,10 +228,24 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st);
+                        cudaStream_t st, float* stats = nullptr);
 int option_pw_pair();
 }
 using namespace ts;
+
+// Training forward: z = W a (bf16 rows, no epilogue) plus per-block BatchNorm partial sums from the GEMM epilogue.
+extern "C" int ts_pw_gemm_stats(const void* w, const void* x, int cin, int x_pitch, int B, int Cout, int T, void* out,
+                                int out_pitch, float* stats, int slots, void* stream) {
+  TS_REQUIRE(w && x && out && stats, TS_ERR_INVALID, "ts_pw_gemm_stats: null pointer");
+  TS_REQUIRE(B > 0 && B <= 65535 && Cout > 0 && T > 0 && cin > 0 && cin % 8 == 0, TS_ERR_INVALID, "ts_pw_gemm_stats: bad sizes");
+  TS_REQUIRE(x_pitch % 8 == 0 && x_pitch >= T && out_pitch % 64 == 0 && out_pitch >= T, TS_ERR_INVALID,
+             "ts_pw_gemm_stats: bad pitches");
+  TS_REQUIRE(slots == 2 * ceil_div(out_pitch, 256), TS_ERR_INVALID,
+             "ts_pw_gemm_stats: slots must be 2 * ceil(out_pitch / 256) (one per 128-frame block)");
+  if (!(option_pw_big() && option_pw_pair() > 0)) return TS_ERR_UNSUPPORTED;
+  return launch_pw_gemm_pair(w, x, cin, x_pitch, nullptr, nullptr, 0, 0, B, Cout, T, nullptr, nullptr, out, out_pitch, 0,
+                             nullptr, nullptr, nullptr, 0, (cudaStream_t)stream, stats);
+}
 
 // Host side: see include/thunder_b200.h for the contract.
 extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1,

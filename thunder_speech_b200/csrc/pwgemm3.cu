@@ -37,6 +37,7 @@ struct Params {
   int m_tiles, n_tiles, num_tiles;
   const float* shift;
   const int32_t* lens;
+  float* stats;        // optional [B, Cout, 2 * n_tiles, 2]: (sum, sum of squares) of the STORED bf16 values per 128-frame block
   int out_pitch;
   int relu;
   float* pool;
@@ -240,6 +241,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const float gate = (m_ok && p.se_scale) ? p.se_scale[(size_t)b * p.Cout + m] : 0.f;
       float pooled = 0.f;
+      float st_s = 0.f, st_ss = 0.f;
       const int a = it % ACC;
       ptx::mbar_wait(&tmem_full[a], (it / ACC) & 1);
       ptx::tc_fence_after();
@@ -299,6 +301,11 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
               const int j = g * 8 + 2 * hh;
               __nv_bfloat162 pr = __floats2bfloat162_rn(r[j], r[j + 1]);
               pk[hh] = *reinterpret_cast<uint32_t*>(&pr);
+              if (p.stats) {
+                const float2 f = __bfloat1622float2(pr);
+                st_s += f.x + f.y;
+                st_ss = fmaf(f.x, f.x, fmaf(f.y, f.y, st_ss));
+              }
             }
             // SWIZZLE_128B: 16-byte chunk g of row `lane` lives at chunk (g ^ (row & 7))
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((g ^ (lane & 7)) << 4)),
@@ -314,6 +321,9 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
         }
       }
       if (p.pool && m_ok) atomicAdd(p.pool + (size_t)b * p.Cout + m, pooled);
+      if (p.stats && m_ok)   // one slot per (row, 128-frame block): written exactly once, no atomics (deterministic)
+        *reinterpret_cast<float2*>(p.stats + ((((size_t)b * p.Cout + m) * (2 * p.n_tiles)) + nt * 2 + h) * 2) =
+            make_float2(st_s, st_ss);
     }
     if (lane == 0) bulk_wait0();   // all stores of this warp are complete before the CTA exits
   }
@@ -331,7 +341,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* stats) {
   if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
   pw3::Params p;
   memset(&p, 0, sizeof(p));
@@ -356,6 +366,7 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   p.n_tiles = ceil_div(out_pitch, pw3::BN);
   p.num_tiles = p.m_tiles * p.n_tiles * B;
   p.shift = shift; p.lens = lens; p.out_pitch = out_pitch; p.relu = relu;
+  p.stats = stats;
   p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
   static int num_sms = 0;
   if (num_sms == 0) {

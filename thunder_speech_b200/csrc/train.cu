@@ -95,17 +95,32 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
 __global__ void __launch_bounds__(RW * 32)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                      const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr, int T, int pitch,
-                     long long rows, int relu, float* __restrict__ sums) {
+                     long long rows, int relu, float* __restrict__ sums, int C, const float* __restrict__ ms,
+                     const float* __restrict__ mh, const float* __restrict__ msr, const float* __restrict__ mhr) {
   const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  // y == nullptr: the ReLU mask is recomputed as (z * ms[c] + mh[c] (+ zr * msr[c] + mhr[c]) > 0), the expression
+  // bn_apply_kernel evaluated in the forward pass -- saves reading y
+  const bool remask = relu && y == nullptr;
+  const int c = (int)(row % C);
+  const float sc = remask ? ms[c] : 0.f, sh = remask ? mh[c] : 0.f;
+  const float sc2 = (remask && zr != nullptr) ? msr[c] : 0.f, sh2 = (remask && zr != nullptr) ? mhr[c] : 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   for (int t = lane * 8; t < T; t += 256) {
     float g[8], yy[8], zz[8], z2[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + row * pitch + t), g);
     unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), zz);
-    if (relu) unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
+    if (relu && !remask) unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
     if (zr != nullptr) unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), z2);
+    if (remask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o = fmaf(zz[j], sc, sh);
+        if (zr != nullptr) o += fmaf(z2[j], sc2, sh2);
+        yy[j] = o;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (t + j < T) {
@@ -131,7 +146,9 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
                                     const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr,
                                     const float* __restrict__ coef, const float* __restrict__ coef_r, int C, int T,
                                     int pitch, int relu, __nv_bfloat16* __restrict__ dz,
-                                    __nv_bfloat16* __restrict__ dzr, long long rows) {
+                                    __nv_bfloat16* __restrict__ dzr, long long rows, const float* __restrict__ ms,
+                                    const float* __restrict__ mh, const float* __restrict__ msr,
+                                    const float* __restrict__ mhr) {
   const long long row = blockIdx.x;
   const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (row >= rows || t >= pitch) return;
@@ -140,7 +157,20 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
   unpack8(*reinterpret_cast<const uint4*>(dy + row * pitch + t), g);
   unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), zz);
   if (relu) {
-    unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
+    if (y != nullptr) {
+      unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
+    } else {   // recompute the forward pre-activation exactly as bn_apply_kernel did
+      const float sc = ms[c], sh = mh[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yy[j] = fmaf(zz[j], sc, sh);
+      if (zr != nullptr) {
+        float z2[8];
+        unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), z2);
+        const float sc2 = msr[c], sh2 = mhr[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] += fmaf(z2[j], sc2, sh2);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (!(yy[j] > 0.f)) g[j] = 0.f;
@@ -235,21 +265,27 @@ extern "C" int ts_bn_apply(const void* z, const float* scale, const float* shift
 }
 
 extern "C" int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, const void* zr, int B, int C, int T,
-                                int pitch, int relu, float* sums, void* stream) {
-  TS_REQUIRE(dy && z && sums && (!relu || y), TS_ERR_INVALID, "ts_bn_bwd_reduce: null pointer");
+                                int pitch, int relu, float* sums, const float* mask_scale, const float* mask_shift,
+                                const float* mask_scale_r, const float* mask_shift_r, void* stream) {
+  TS_REQUIRE(dy && z && sums, TS_ERR_INVALID, "ts_bn_bwd_reduce: null pointer");
+  TS_REQUIRE(!relu || y || (mask_scale && mask_shift && (!zr || (mask_scale_r && mask_shift_r))), TS_ERR_INVALID,
+             "ts_bn_bwd_reduce: relu needs y or the forward scale/shift to rebuild the mask");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_reduce: bad sizes");
   const long long rows = (long long)B * C;
   train::bn_bwd_reduce_kernel<<<(unsigned)ceil_div64(rows, train::RW), train::RW * 32, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, T, pitch, rows,
-      relu, sums);
+      relu, sums, C, mask_scale, mask_shift, mask_scale_r, mask_shift_r);
   TS_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return TS_OK;
 }
 
 extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, const void* zr, const float* coef,
                                const float* coef_r, int B, int C, int T, int pitch, int relu, void* dz, void* dzr,
-                               void* stream) {
-  TS_REQUIRE(dy && z && coef && dz && (!relu || y), TS_ERR_INVALID, "ts_bn_bwd_apply: null pointer");
+                               const float* mask_scale, const float* mask_shift, const float* mask_scale_r,
+                               const float* mask_shift_r, void* stream) {
+  TS_REQUIRE(dy && z && coef && dz, TS_ERR_INVALID, "ts_bn_bwd_apply: null pointer");
+  TS_REQUIRE(!relu || y || (mask_scale && mask_shift && (!zr || (mask_scale_r && mask_shift_r))), TS_ERR_INVALID,
+             "ts_bn_bwd_apply: relu needs y or the forward scale/shift to rebuild the mask");
   TS_REQUIRE((zr == nullptr) == (coef_r == nullptr) && (zr == nullptr) == (dzr == nullptr), TS_ERR_INVALID,
              "ts_bn_bwd_apply: residual operands disagree");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_apply: bad sizes");
@@ -258,7 +294,7 @@ extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, con
   dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
   train::bn_bwd_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, coef, coef_r, C,
-      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows);
+      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows, mask_scale, mask_shift, mask_scale_r, mask_shift_r);
   TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TS_OK;
 }
@@ -267,15 +303,17 @@ namespace ts {
 namespace train {
 
 // One warp per channel: lanes stride over the NB partials (independent loads), shuffle-reduce in double.
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int NB, int C, double n, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int NB, int slots, int C, double n,
+                                   const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ inv_out) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = lane; b < NB; b += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)b * C + c) * 2);
+  for (int i = lane; i < NB * slots; i += 32) {   // part[b, c, slot, 2]
+    const int b = i / slots, sl = i - b * slots;
+    const float2 v = *reinterpret_cast<const float2*>(part + (((size_t)b * C + c) * slots + sl) * 2);
     s0 += v.x;
     s1 += v.y;
   }
@@ -333,13 +371,13 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ part, int NB, int C
 }  // namespace train
 }  // namespace ts
 
-extern "C" int ts_bn_finalize(const float* part, int NB, int C, double n, const float* gamma, const float* beta, float eps,
+extern "C" int ts_bn_finalize(const float* part, int NB, int slots, int C, double n, const float* gamma, const float* beta, float eps,
                               float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                               float* mean, float* inv, void* stream) {
   TS_REQUIRE(part && gamma && beta && scale && shift && mean && inv, TS_ERR_INVALID, "ts_bn_finalize: null pointer");
-  TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID,
+  TS_REQUIRE(NB > 0 && slots > 0 && C > 0 && n >= 1.0 && (running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID,
              "ts_bn_finalize: bad sizes");
-  train::bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, C, n, gamma, beta, eps, momentum,
+  train::bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, slots, C, n, gamma, beta, eps, momentum,
                                                                                running_mean, running_var, scale, shift,
                                                                                mean, inv);
   TS_LAUNCH_CHECK("bn_finalize_kernel");

@@ -58,14 +58,35 @@ def row_stats_partial(z: Tensor, T: int) -> Tensor:
     return st
 
 
+def pw_gemm_stats(w: Tensor, x: Tensor, T: int) -> Tuple[Tensor, Tensor]:
+    """z = W x (bf16 rows) and the BatchNorm partial sums of z, [B, Cout, slots, 2].  Cout > 128: the statistics come out
+    of the GEMM epilogue (ts_pw_gemm_stats); otherwise a plain GEMM followed by ts_row_stats (slots = 1)."""
+    B, cin, px = x.shape
+    Cout = w.shape[0]
+    if Cout > 128:
+        pitch = ops.row_pitch(T)
+        slots = 2 * ((pitch + 255) // 256)
+        z = torch.empty((B, Cout, pitch), device=x.device, dtype=torch.bfloat16)
+        st = torch.empty((B, Cout, slots, 2), device=x.device, dtype=torch.float32)
+        with ops._timed("pw_gemm", bytes=2 * B * T * (cin + Cout) + 2 * Cout * cin, flops=2 * B * T * cin * Cout, K=cin,
+                        C=Cout, T=T):
+            rc = _lib.lib().ts_pw_gemm_stats(_p(w), _p(x), cin, px, B, Cout, T, _p(z), pitch, _p(st), slots, _stream())
+        if rc != _lib.TS_ERR_UNSUPPORTED:
+            _lib.check(rc, "ts_pw_gemm_stats")
+            return z, st
+    z = ops.pw_gemm(w, x, None, None, T, None, None, False, False, None, None, None)
+    return z, row_stats_partial(z, T).unsqueeze(2)
+
+
 def bn_finalize(part: Tensor, n: int, bn: nn.BatchNorm1d, update_running: bool):
-    """(scale, shift, mean, inv) f32 [C] from the partial sums, on the device; updates the running statistics in place like
-    nn.BatchNorm1d(momentum) does in train() (unbiased variance for the running estimate)."""
-    NB, C, _ = part.shape
+    """(scale, shift, mean, inv) f32 [C] from the partial sums [NB, C, 2] or [NB, C, slots, 2], on the device; updates the
+    running statistics in place like nn.BatchNorm1d(momentum) does in train() (unbiased variance for the running estimate)."""
+    NB, C = part.shape[0], part.shape[1]
+    slots = part.shape[2] if part.dim() == 4 else 1
     out = torch.empty((4, C), device=part.device, dtype=torch.float32)
     upd = update_running and bn.track_running_stats
     m = bn.momentum if bn.momentum is not None else BN_MOMENTUM
-    _lib.check(_lib.lib().ts_bn_finalize(_p(part), NB, C, float(n), _p(bn.weight), _p(bn.bias), float(bn.eps), float(m),
+    _lib.check(_lib.lib().ts_bn_finalize(_p(part), NB, slots, C, float(n), _p(bn.weight), _p(bn.bias), float(bn.eps), float(m),
                                          _p(bn.running_mean) if upd else None, _p(bn.running_var) if upd else None,
                                          _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _stream()), "ts_bn_finalize")
     return out[0], out[1], out[2], out[3]
@@ -110,22 +131,27 @@ def bn_apply(z, scale, shift, zr, scale_r, shift_r, T, lens, relu=True) -> Tenso
     return y
 
 
-def bn_bwd_reduce(dy, y, z, zr, T, relu=True, partial: bool = False) -> Tensor:
+def bn_bwd_reduce(dy, y, z, zr, T, relu=True, partial: bool = False, mask=None) -> Tensor:
+    """``mask`` = (scale, shift, scale_r, shift_r) of the forward bn_apply: with ``y=None`` the ReLU mask is rebuilt from
+    z (and zr) instead of being read from y."""
     B, C, pitch = z.shape
+    ms = mask if mask is not None else (None, None, None, None)
     sums = torch.empty((B, C, 3), device=z.device, dtype=torch.float32)
     with ops._timed("bn_bwd_reduce", bytes=B * C * T * 2 * (4 if zr is not None else 3), flops=0):
         _lib.check(_lib.lib().ts_bn_bwd_reduce(_p(dy), _p(y), _p(z), _p(zr), B, C, T, pitch, int(relu), _p(sums),
-                                               _stream()), "ts_bn_bwd_reduce")
+                                               _p(ms[0]), _p(ms[1]), _p(ms[2]), _p(ms[3]), _stream()), "ts_bn_bwd_reduce")
     return sums if partial else sums.sum(0, dtype=torch.float64)
 
 
-def bn_bwd_apply(dy, y, z, zr, coef, coef_r, T, relu=True) -> Tuple[Tensor, Optional[Tensor]]:
+def bn_bwd_apply(dy, y, z, zr, coef, coef_r, T, relu=True, mask=None) -> Tuple[Tensor, Optional[Tensor]]:
     B, C, pitch = z.shape
+    ms = mask if mask is not None else (None, None, None, None)
     dz = torch.empty_like(z)
     dzr = torch.empty_like(z) if zr is not None else None
     with ops._timed("bn_bwd_apply", bytes=B * C * T * 2 * (6 if zr is not None else 4), flops=0):
         _lib.check(_lib.lib().ts_bn_bwd_apply(_p(dy), _p(y), _p(z), _p(zr), _p(coef), _p(coef_r), B, C, T, pitch,
-                                              int(relu), _p(dz), _p(dzr), _stream()), "ts_bn_bwd_apply")
+                                              int(relu), _p(dz), _p(dzr), _p(ms[0]), _p(ms[1]), _p(ms[2]), _p(ms[3]),
+                                              _stream()), "ts_bn_bwd_apply")
     return dz, dzr
 
 
@@ -246,6 +272,39 @@ class WeightPack:
         return self.views[id(p)]
 
 
+class _SideStream:
+    """Weight gradients are off the critical path of the backward pass (which is the dx chain: BN backward -> W^T GEMM ->
+    flipped-tap depthwise conv).  They are issued on a second stream, forked and joined with events, so that inside the
+    captured CUDA graph they become parallel branches that fill the SMs left idle by the small per-layer kernels.
+    Tensors handed to the side stream are kept alive until the join (no allocator reuse while a side kernel is pending)."""
+
+    _streams: Dict[int, "torch.cuda.Stream"] = {}
+
+    def __init__(self, device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in _SideStream._streams:
+            _SideStream._streams[idx] = torch.cuda.Stream(device=idx)
+        self.stream = _SideStream._streams[idx]
+        self.keep: List[Tensor] = []
+        self.dirty = False
+
+    def run(self, fn, *tensors: Tensor) -> None:
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.keep.extend(t for t in tensors if t is not None)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            fn()
+        self.dirty = True
+
+    def join(self) -> None:
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.dirty = False
+        self.keep.clear()
+
+
 class BlockTrainer:
     """train()-mode forward / backward of one QuartznetBlock on bf16 rows."""
 
@@ -312,17 +371,18 @@ class BlockTrainer:
             else:
                 a, Ta, la = cur, Tc, lc
             wpw = self.pack.get(sb.pw.weight)[0]
-            z = ops.pw_gemm(wpw, a, None, None, Ta, None, None, False, False, None, None, None)
+            z, zst = pw_gemm_stats(wpw, a, Ta)
             nn_ = B * Ta
-            scale, shift, mean, inv = bn_finalize(row_stats_partial(z, Ta), nn_, sb.bn, update_running)
-            rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, mean=mean, inv=inv, n=nn_, wpw=wpw)
+            scale, shift, mean, inv = bn_finalize(zst, nn_, sb.bn, update_running)
+            rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, mean=mean, inv=inv, n=nn_,
+                       mask=(scale, shift, None, None))
             if last and self.res is not None:
                 rconv, rbn = self.res
                 wr = self.pack.get(rconv.weight)[0]
-                zr = ops.pw_gemm(wr, x, None, None, T, None, None, False, False, None, None, None)
-                scale_r, shift_r, mean_r, inv_r = bn_finalize(row_stats_partial(zr, T), B * T, rbn, update_running)
+                zr, zrst = pw_gemm_stats(wr, x, T)
+                scale_r, shift_r, mean_r, inv_r = bn_finalize(zrst, B * T, rbn, update_running)
                 y = bn_apply(z, scale, shift, zr, scale_r, shift_r, Ta, la if zero_tail else None, True)
-                rec.update(zr=zr, mean_r=mean_r, inv_r=inv_r, wr=wr)
+                rec.update(zr=zr, mean_r=mean_r, inv_r=inv_r, mask=(scale, shift, scale_r, shift_r))
             else:
                 tail = la if (not last or zero_tail) else None
                 y = bn_apply(z, scale, shift, None, None, None, Ta, tail, True)
@@ -338,7 +398,11 @@ class BlockTrainer:
         return y, Tc, lc, tape
 
     # -- backward --------------------------------------------------------------------------------------
-    def backward(self, tape, dy: Tensor, need_dx: bool = True) -> Optional[Tensor]:
+    def backward(self, tape, dy: Tensor, need_dx: bool = True, side: Optional[_SideStream] = None) -> Optional[Tensor]:
+        """``side``: the caller's side stream (the caller joins it); None = own side stream, joined before returning."""
+        own_side = side is None
+        if own_side:
+            side = _SideStream(dy.device)
         n = len(self.subs)
         dx_res = None
         g = dy
@@ -347,15 +411,18 @@ class BlockTrainer:
             last = r == n - 1
             has_res = last and self.res is not None
             Ta = rec["Ta"]
-            sums = bn_bwd_reduce(g, rec["y"], rec["z"], rec.get("zr") if has_res else None, Ta, True, partial=True)
+            # the ReLU mask is rebuilt from z with the forward scale / shift (y is not read again)
+            sums = bn_bwd_reduce(g, None, rec["z"], rec.get("zr") if has_res else None, Ta, True, partial=True,
+                                 mask=rec["mask"])
             coef = bn_bwd_coef(sums, 1, rec["n"], sb.bn, rec["mean"], rec["inv"])
             coef_r = None
             if has_res:
                 rconv, rbn = self.res
                 coef_r = bn_bwd_coef(sums, 2, rec["n"], rbn, rec["mean_r"], rec["inv_r"])
-            dz, dzr = bn_bwd_apply(g, rec["y"], rec["z"], rec.get("zr") if has_res else None, coef, coef_r, Ta, True)
+            dz, dzr = bn_bwd_apply(g, None, rec["z"], rec.get("zr") if has_res else None, coef, coef_r, Ta, True,
+                                   mask=rec["mask"])
             # pointwise conv: weight gradient on the tensor cores, input gradient = W^T dz (masked like `a` was)
-            pw_wgrad(dz, rec["a"], Ta, out=_grad(sb.pw.weight))
+            side.run(lambda dz=dz, rec=rec, sb=sb, Ta=Ta: pw_wgrad(dz, rec["a"], Ta, out=_grad(sb.pw.weight)), dz)
             first = r == 0
             need_da = sb.dw is not None or need_dx or not first
             da = None
@@ -363,8 +430,9 @@ class BlockTrainer:
                 wT = self.pack.get(sb.pw.weight)[1]
                 da = ops.pw_gemm(wT, dz, None, None, Ta, None, rec["la"], False, False, None, None, None)
             if sb.dw is not None:
-                dw_wgrad(da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight),
-                         premasked=True)
+                side.run(lambda da=da, rec=rec, sb=sb, Ta=Ta: dw_wgrad(
+                    da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight),
+                    premasked=True), da)
                 if (not first) or need_dx:
                     if sb.S != 1:
                         raise NotImplementedError("training step: input gradient of a strided depthwise conv")
@@ -376,7 +444,7 @@ class BlockTrainer:
                 g = da
             if has_res:
                 rconv, rbn = self.res
-                pw_wgrad(dzr, tape["x"], tape["T"], out=_grad(rconv.weight))
+                side.run(lambda dzr=dzr, rconv=rconv: pw_wgrad(dzr, tape["x"], tape["T"], out=_grad(rconv.weight)), dzr)
                 if need_dx:
                     dx_res = dzr
         if need_dx and self.res is not None:
@@ -385,6 +453,8 @@ class BlockTrainer:
             wrT = self.pack.get(rconv.weight)[1]
             ones = torch.ones((g.shape[0], wrT.shape[0]), device=g.device, dtype=torch.float32)
             g = ops.pw_gemm(wrT, dx_res, None, None, tape["T"], None, tape["lens"], False, False, None, ones, g)
+        if own_side:
+            side.join()
         return g if need_dx else None
 
 
@@ -415,10 +485,15 @@ class EncoderTrainer:
             tapes.append(tape)
         return rows, T, lens, tapes
 
-    def backward(self, tapes, dy: Tensor) -> None:
+    def backward(self, tapes, dy: Tensor, side: Optional[_SideStream] = None) -> None:
+        own_side = side is None
+        if own_side:
+            side = _SideStream(dy.device)
         g = dy
         for i in range(len(self.blocks) - 1, -1, -1):
-            g = self.blocks[i].backward(tapes[i], g, need_dx=(i > 0))
+            g = self.blocks[i].backward(tapes[i], g, need_dx=(i > 0), side=side)
+        if own_side:
+            side.join()
 
 
 class _StepGraph:
