@@ -21,7 +21,7 @@ static std::atomic<int> g_opt_dw_mma{1};
 static std::atomic<int> g_opt_pw_big{1};
 static std::atomic<int> g_opt_dw_tma{1};
 static std::atomic<int> g_opt_pw_bn{0};
-static std::atomic<int> g_opt_pdl{0};
+static std::atomic<int> g_opt_pdl{3};
 int option_pdl() { return g_opt_pdl.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_pw_pair{2};
 int option_pw_pair() { return g_opt_pw_pair.load(std::memory_order_relaxed); }

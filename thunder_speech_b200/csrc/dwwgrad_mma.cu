@@ -103,6 +103,8 @@ dw_wgrad_mma_kernel(const __grid_constant__ Params p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = p.NQ * 64;
+  pdl_launch_dependents();   // PDL: the prologue above overlapped the previous kernel's tail
+  pdl_wait();                // its outputs (da, x) are complete and visible from here on
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -252,7 +254,7 @@ int launch_dw_wgrad_mma(const __nv_bfloat16* da, int pitch_out, const __nv_bfloa
     attr_set = true;
   }
   const int grid = C < 148 ? C : 148;
-  dwg::dw_wgrad_mma_kernel<<<grid, dwg::THREADS, dwg::SMEM_BYTES, st>>>(p);
+  TS_CUDA(launch_pdl(dwg::dw_wgrad_mma_kernel, dim3(grid), dim3(dwg::THREADS), dwg::SMEM_BYTES, st, (option_pdl() & 2) != 0, p));
   TS_LAUNCH_CHECK("dw_wgrad_mma_kernel");
   return TS_OK;
 }

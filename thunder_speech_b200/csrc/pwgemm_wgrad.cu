@@ -65,6 +65,8 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // PDL: the prologue above overlapped the previous kernel's tail
+  pdl_wait();                // its outputs (dz, a) are complete and visible from here on
 
   if (warp == 0 && lane == 0) {
     for (int kc = 0; kc < num_k; ++kc) {
@@ -140,6 +142,8 @@ pw_wgrad_kernel(const __grid_constant__ Params p) {
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ part, int nsplit, long long n4, float4* __restrict__ out) {
   __shared__ float4 sm[8][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + lane;
   const int per = (nsplit + 7) >> 3;
@@ -203,7 +207,7 @@ extern "C" int ts_pw_wgrad(const void* dz, int dz_pitch, const void* a, int a_pi
     attr_set = true;
   }
   dim3 grid(ceil_div(Cout, wg::BM), ceil_div(Cin, wg::BN), nsplit);
-  wg::pw_wgrad_kernel<<<grid, 256, wg::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  TS_CUDA(launch_pdl(wg::pw_wgrad_kernel, grid, dim3(256), wg::SMEM_BYTES, (cudaStream_t)stream, (option_pdl() & 2) != 0, p));
   TS_LAUNCH_CHECK("pw_wgrad_kernel");
   return TS_OK;
 }
@@ -213,8 +217,8 @@ extern "C" int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, fl
   TS_REQUIRE(nsplit > 0 && n > 0 && n % 4 == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: n must be a positive multiple of 4");
   TS_REQUIRE((((uintptr_t)part | (uintptr_t)out) & 15) == 0, TS_ERR_INVALID, "ts_pw_wgrad_reduce: 16-byte alignment required");
   const long long n4 = n / 4;
-  wg::wgrad_reduce_kernel<<<(unsigned)ceil_div64(n4, 32), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(part), nsplit, n4, reinterpret_cast<float4*>(out));
+  TS_CUDA(launch_pdl(wg::wgrad_reduce_kernel, dim3((unsigned)ceil_div64(n4, 32)), dim3(256), 0, (cudaStream_t)stream,
+                     (option_pdl() & 2) != 0, reinterpret_cast<const float4*>(part), nsplit, n4, reinterpret_cast<float4*>(out)));
   TS_LAUNCH_CHECK("wgrad_reduce_kernel");
   return TS_OK;
 }

@@ -41,6 +41,8 @@ constexpr int RW = 8;  // warps per CTA for the row kernels
 // stats[row] = (sum_t z, sum_t z^2) over t < T, one warp per (b, c) row
 __global__ void __launch_bounds__(RW * 32)
 row_stats_kernel(const __nv_bfloat16* __restrict__ z, int T, int pitch, long long rows, float2* __restrict__ stats) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -67,6 +69,8 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
                                 const float* __restrict__ sr, const float* __restrict__ hr, int C, int T, int pitch,
                                 const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ y,
                                 long long rows) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const long long row = blockIdx.x;
   const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (row >= rows || t >= pitch) return;
@@ -97,6 +101,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr, int T, int pitch,
                      long long rows, int relu, float* __restrict__ sums, int C, const float* __restrict__ ms,
                      const float* __restrict__ mh, const float* __restrict__ msr, const float* __restrict__ mhr) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -149,6 +155,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
                                     __nv_bfloat16* __restrict__ dzr, long long rows, const float* __restrict__ ms,
                                     const float* __restrict__ mh, const float* __restrict__ msr,
                                     const float* __restrict__ mhr) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const long long row = blockIdx.x;
   const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (row >= rows || t >= pitch) return;
@@ -241,8 +249,8 @@ extern "C" int ts_row_stats(const void* z, int B, int C, int T, int pitch, float
   TS_REQUIRE(z && stats, TS_ERR_INVALID, "ts_row_stats: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_row_stats: bad sizes");
   const long long rows = (long long)B * C;
-  train::row_stats_kernel<<<(unsigned)ceil_div64(rows, train::RW), train::RW * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)z, T, pitch, rows, (float2*)stats);
+  TS_CUDA(launch_pdl(train::row_stats_kernel, dim3((unsigned)ceil_div64(rows, train::RW)), dim3(train::RW * 32), 0,
+                     (cudaStream_t)stream, (option_pdl() & 2) != 0, (const __nv_bfloat16*)z, T, pitch, rows, (float2*)stats));
   TS_LAUNCH_CHECK("row_stats_kernel");
   return TS_OK;
 }
@@ -257,9 +265,10 @@ extern "C" int ts_bn_apply(const void* z, const float* scale, const float* shift
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_apply: too many rows");
   dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
-  train::bn_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift,
+  TS_CUDA(launch_pdl(train::bn_apply_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     (const __nv_bfloat16*)z, scale, shift,
                                                                  (const __nv_bfloat16*)zr, scale_r, shift_r, C, T, pitch,
-                                                                 lens, relu, (__nv_bfloat16*)y, rows);
+                                                                 lens, relu, (__nv_bfloat16*)y, rows));
   TS_LAUNCH_CHECK("bn_apply_kernel");
   return TS_OK;
 }
@@ -272,9 +281,10 @@ extern "C" int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, co
              "ts_bn_bwd_reduce: relu needs y or the forward scale/shift to rebuild the mask");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_reduce: bad sizes");
   const long long rows = (long long)B * C;
-  train::bn_bwd_reduce_kernel<<<(unsigned)ceil_div64(rows, train::RW), train::RW * 32, 0, (cudaStream_t)stream>>>(
+  TS_CUDA(launch_pdl(train::bn_bwd_reduce_kernel, dim3((unsigned)ceil_div64(rows, train::RW)), dim3(train::RW * 32), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, T, pitch, rows,
-      relu, sums, C, mask_scale, mask_shift, mask_scale_r, mask_shift_r);
+      relu, sums, C, mask_scale, mask_shift, mask_scale_r, mask_shift_r));
   TS_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return TS_OK;
 }
@@ -292,9 +302,10 @@ extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, con
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_bwd_apply: too many rows");
   dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
-  train::bn_bwd_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+  TS_CUDA(launch_pdl(train::bn_bwd_apply_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, coef, coef_r, C,
-      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows, mask_scale, mask_shift, mask_scale_r, mask_shift_r);
+      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows, mask_scale, mask_shift, mask_scale_r, mask_shift_r));
   TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TS_OK;
 }
@@ -308,6 +319,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int NB, int s
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ inv_out) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
@@ -342,6 +355,8 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ part, int NB, int C
                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                    const float* __restrict__ inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                    float* __restrict__ coef) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
@@ -377,9 +392,10 @@ extern "C" int ts_bn_finalize(const float* part, int NB, int slots, int C, doubl
   TS_REQUIRE(part && gamma && beta && scale && shift && mean && inv, TS_ERR_INVALID, "ts_bn_finalize: null pointer");
   TS_REQUIRE(NB > 0 && slots > 0 && C > 0 && n >= 1.0 && (running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID,
              "ts_bn_finalize: bad sizes");
-  train::bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, slots, C, n, gamma, beta, eps, momentum,
+  TS_CUDA(launch_pdl(train::bn_finalize_kernel, dim3(ceil_div(C, 4)), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     part, NB, slots, C, n, gamma, beta, eps, momentum,
                                                                                running_mean, running_var, scale, shift,
-                                                                               mean, inv);
+                                                                               mean, inv));
   TS_LAUNCH_CHECK("bn_finalize_kernel");
   return TS_OK;
 }
@@ -388,8 +404,9 @@ extern "C" int ts_bn_bwd_coef(const float* part, int NB, int C, int which, doubl
                               const float* inv, float* dgamma, float* dbeta, float* coef, void* stream) {
   TS_REQUIRE(part && gamma && mean && inv && dgamma && dbeta && coef, TS_ERR_INVALID, "ts_bn_bwd_coef: null pointer");
   TS_REQUIRE(NB > 0 && C > 0 && n >= 1.0 && (which == 1 || which == 2), TS_ERR_INVALID, "ts_bn_bwd_coef: bad arguments");
-  train::bn_bwd_coef_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(part, NB, C, which, n, gamma, mean, inv,
-                                                                               dgamma, dbeta, coef);
+  TS_CUDA(launch_pdl(train::bn_bwd_coef_kernel, dim3(ceil_div(C, 4)), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     part, NB, C, which, n, gamma, mean, inv,
+                                                                               dgamma, dbeta, coef));
   TS_LAUNCH_CHECK("bn_bwd_coef_kernel");
   return TS_OK;
 }
@@ -404,6 +421,8 @@ namespace train {
 // Tiles are 32 x 32; a CTA finds its table row by binary search over first_tile.
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const long long* __restrict__ tab, int n) {
+  pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
+  pdl_wait();
   __shared__ float tile[32][33];
   int lo = 0, hi = n - 1;
   while (lo < hi) {
@@ -458,7 +477,8 @@ prep_weights_kernel(const long long* __restrict__ tab, int n) {
 extern "C" int ts_prep_weights(const long long* table, int n_entries, long long total_tiles, void* stream) {
   TS_REQUIRE(table != nullptr && n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), TS_ERR_INVALID,
              "ts_prep_weights: bad arguments");
-  train::prep_weights_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(table, n_entries);
+  TS_CUDA(launch_pdl(train::prep_weights_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     table, n_entries));
   TS_LAUNCH_CHECK("prep_weights_kernel");
   return TS_OK;
 }

@@ -54,7 +54,7 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 constexpr int kRowPitchAlign = 64;  // frames; 128 bytes of bf16
 
-int option_pdl();  // 1: hot kernels are launched with programmatic stream serialization (PDL)
+int option_pdl();  // bit 0: the hot inference kernels (pair GEMM, Toeplitz conv) launch with programmatic stream serialization (PDL); bit 1: the training-step kernels too
 
 // ---- programmatic dependent launch --------------------------------------------------------------
 // Device side: `pdl_launch_dependents()` lets the NEXT kernel in the stream start its prologue as soon as every CTA of
