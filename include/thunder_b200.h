@@ -200,6 +200,20 @@ int ts_pw_gemm_stats(const void* w, const void* x, int cin, int x_pitch, int B, 
 int ts_bn_finalize(const float* part, int NB, int slots, int C, double n, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
                    float* inv, void* stream);
+/* Fused ts_bn_finalize + ts_bn_apply (one CTA per channel reduces the partial sums, then streams the B rows):
+ * y = act(BN(z) [+ BN_r(zr)]) with train()-mode batch statistics over n = B * T positions; stats_out [4, C] = (scale,
+ * shift, mean, inv) per branch for the backward pass; running statistics (nullable) updated in place. */
+int ts_bn_apply_fused(const void* z, const float* part, int NB, int slots, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* stats_out, const void* zr, const float* part_r,
+                      int NB_r, int slots_r, const float* gamma_r, const float* beta_r, float* running_mean_r,
+                      float* running_var_r, float* stats_out_r, float eps, float momentum, int B, int C, int T, int pitch,
+                      const int32_t* lens, int relu, void* y, void* stream);
+/* Fused ts_bn_bwd_coef + ts_bn_bwd_apply: from sums [B, C, 3] (ts_bn_bwd_reduce) and the forward stats [4, C], writes
+ * dgamma / dbeta [C] and dz (dzr) = a dym + b z + c0 with the ReLU mask rebuilt from z (zr). */
+int ts_bn_bwd_apply_fused(const void* dy, const void* z, const float* gamma, const float* stats, float* dgamma,
+                          float* dbeta, void* dz, const void* zr, const float* gamma_r, const float* stats_r,
+                          float* dgamma_r, float* dbeta_r, void* dzr, const float* sums, int B, int C, int T, int pitch,
+                          int relu, void* stream);
 /* BatchNorm backward coefficients from the partial sums of ts_bn_bwd_reduce (part [NB, C, 3]; `which` = 1 for the main
  * branch (sum dym*z), 2 for the residual branch (sum dym*zr)): dbeta = sum dym, dgamma = inv (sum dym*z - mean sum dym),
  * coef[c] = (a, b, c0) with dz = a dym + b z + c0 (see ts_bn_bwd_apply) */

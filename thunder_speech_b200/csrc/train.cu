@@ -13,6 +13,8 @@
 //     dx = dw^T(da) (Toeplitz kernel with flipped taps).
 // All tensors are bf16 rows [B, C, pitch]; reductions accumulate in fp32 and are written per (b, c) row (deterministic),
 // the final sum over the batch is a tiny host-side torch reduction.
+#include <algorithm>
+
 #include "ts_common.cuh"
 
 namespace ts {
@@ -473,6 +475,226 @@ prep_weights_kernel(const long long* __restrict__ tab, int n) {
 
 }  // namespace train
 }  // namespace ts
+
+namespace ts {
+namespace train {
+
+// block-wide sum of two doubles (256 threads); result valid in every thread
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sm /*[16]*/) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) {
+    sm[w] = a;
+    sm[8 + w] = b;
+  }
+  __syncthreads();
+  a = 0.0;
+  b = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a += sm[i];
+    b += sm[8 + i];
+  }
+}
+
+struct BnSide {          // one BatchNorm branch of the fused forward kernel
+  const __nv_bfloat16* z;
+  const float* part;     // [NB, C, slots, 2]
+  int NB, slots;
+  const float* gamma;
+  const float* beta;
+  float* rmean;          // nullable: running statistics updated in place
+  float* rvar;
+  float* out;            // [4, C]: scale, shift, mean, inv (consumed by the backward pass)
+  float eps, momentum;
+};
+
+// Fused BatchNorm finalize + apply: one CTA per (channel, 2048-frame chunk).  The CTA reduces the partial sums of its
+// channel once (double), derives scale / shift, and then streams all B rows of the channel:
+//   y = act(z * scale + shift (+ zr * scale_r + shift_r)), frames >= lens[b] and the pad stored as zero.
+// blockIdx.y == 0 also publishes (scale, shift, mean, inv) and updates the running statistics.
+__global__ void __launch_bounds__(256)
+bn_apply_fused_kernel(BnSide m, BnSide r, int has_res, int B, int C, int T, int pitch, double n,
+                      const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ y) {
+  __shared__ double red[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x;
+  float sc[2] = {0.f, 0.f}, sh[2] = {0.f, 0.f};
+  for (int side = 0; side < 1 + has_res; ++side) {
+    const BnSide& q = side == 0 ? m : r;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < q.NB * q.slots; i += 256) {
+      const int b = i / q.slots, sl = i - b * q.slots;
+      const float2 v = *reinterpret_cast<const float2*>(q.part + (((size_t)b * C + c) * q.slots + sl) * 2);
+      s0 += v.x;
+      s1 += v.y;
+    }
+    block_sum2(s0, s1, red);
+    const double mean = s0 / n;
+    double var = s1 / n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double inv = 1.0 / sqrt(var + (double)q.eps);
+    const double scd = (double)q.gamma[c] * inv;
+    sc[side] = (float)scd;
+    sh[side] = (float)((double)q.beta[c] - mean * scd);
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+      q.out[c] = sc[side];
+      q.out[C + c] = sh[side];
+      q.out[2 * C + c] = (float)mean;
+      q.out[3 * C + c] = (float)inv;
+      if (q.rmean != nullptr) {
+        q.rmean[c] = (1.f - q.momentum) * q.rmean[c] + q.momentum * (float)mean;
+        q.rvar[c] = (1.f - q.momentum) * q.rvar[c] + q.momentum * (float)(var * n / (n > 1.0 ? n - 1.0 : 1.0));
+      }
+    }
+  }
+  // stream the channel: the B x pitch/8 vectors are flattened so that all 256 threads stay busy for any pitch
+  const int pv = pitch >> 3, total = B * pv;
+  const int per = (total + gridDim.y - 1) / gridDim.y;
+  const int i1 = min(total, (int)(blockIdx.y + 1) * per);
+  for (int i = blockIdx.y * per + threadIdx.x; i < i1; i += 256) {
+    const int b = i / pv, t = (i - b * pv) << 3;
+    const size_t off = ((size_t)b * C + c) * pitch + t;
+    const int lim = lens ? min(T, max(lens[b], 0)) : T;
+    float v[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(m.z + off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sc[0], sh[0]);
+    if (has_res) {
+      unpack8(*reinterpret_cast<const uint4*>(r.z + off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += fmaf(v[j], sc[1], sh[1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (relu) o[j] = fmaxf(o[j], 0.f);
+      if (t + j >= lim) o[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(y + off) = pack8(o);
+  }
+}
+
+struct BnBwdSide {
+  const __nv_bfloat16* z;
+  const float* gamma;
+  const float* stats;    // [4, C] from the forward pass: scale, shift, mean, inv
+  float* dgamma;
+  float* dbeta;
+  __nv_bfloat16* dz;
+};
+
+// Fused BatchNorm backward coefficients + apply: one CTA per (channel, 2048-frame chunk).  From the partial sums of
+// ts_bn_bwd_reduce (sums [B, C, 3]) the CTA derives dgamma, dbeta and the coefficients of dz = a dym + b z + c0 for its
+// channel, then streams all B rows.  The ReLU mask is rebuilt from z (and zr) with the forward scale / shift.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_kernel(const __nv_bfloat16* __restrict__ dy, BnBwdSide m, BnBwdSide r, int has_res,
+                          const float* __restrict__ sums, int B, int C, int T, int pitch, double n, int relu) {
+  __shared__ double red[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float* p = sums + ((size_t)b * C + c) * 3;
+    s0 += p[0];
+    s1 += p[1];
+    s2 += p[2];
+  }
+  block_sum2(s0, s1, red);
+  if (has_res) block_sum2(s2, dummy, red);
+  float ca[2], cb[2], cc[2], sc[2], sh[2];
+  for (int side = 0; side < 1 + has_res; ++side) {
+    const BnBwdSide& q = side == 0 ? m : r;
+    const double mean = q.stats[2 * C + c], iv = q.stats[3 * C + c], g = q.gamma[c];
+    const double sx = side == 0 ? s1 : s2;
+    const double dg = iv * (sx - mean * s0);
+    const double a = g * iv;
+    const double b2 = -g * iv * iv * dg / n;
+    ca[side] = (float)a;
+    cb[side] = (float)b2;
+    cc[side] = (float)(-a * s0 / n - b2 * mean);
+    sc[side] = q.stats[c];
+    sh[side] = q.stats[C + c];
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+      q.dgamma[c] = (float)dg;
+      q.dbeta[c] = (float)s0;
+    }
+  }
+  const int pv = pitch >> 3, total = B * pv;
+  const int per = (total + gridDim.y - 1) / gridDim.y;
+  const int i1 = min(total, (int)(blockIdx.y + 1) * per);
+  for (int i = blockIdx.y * per + threadIdx.x; i < i1; i += 256) {
+    const int b = i / pv, t = (i - b * pv) << 3;
+    const size_t off = ((size_t)b * C + c) * pitch + t;
+    float g[8], zz[8], z2[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + off), g);
+    unpack8(*reinterpret_cast<const uint4*>(m.z + off), zz);
+    if (has_res) unpack8(*reinterpret_cast<const uint4*>(r.z + off), z2);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float pre = fmaf(zz[j], sc[0], sh[0]);
+        if (has_res) pre += fmaf(z2[j], sc[1], sh[1]);
+        if (!(pre > 0.f)) g[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(ca[0], g[j], fmaf(cb[0], zz[j], cc[0])) : 0.f;
+    *reinterpret_cast<uint4*>(m.dz + off) = pack8(o);
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(ca[1], g[j], fmaf(cb[1], z2[j], cc[1])) : 0.f;
+      *reinterpret_cast<uint4*>(r.dz + off) = pack8(o);
+    }
+  }
+}
+
+}  // namespace train
+}  // namespace ts
+
+extern "C" int ts_bn_apply_fused(const void* z, const float* part, int NB, int slots, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, float* stats_out, const void* zr,
+                                 const float* part_r, int NB_r, int slots_r, const float* gamma_r, const float* beta_r,
+                                 float* running_mean_r, float* running_var_r, float* stats_out_r, float eps,
+                                 float momentum, int B, int C, int T, int pitch, const int32_t* lens, int relu, void* y,
+                                 void* stream) {
+  TS_REQUIRE(z && part && gamma && beta && stats_out && y, TS_ERR_INVALID, "ts_bn_apply_fused: null pointer");
+  TS_REQUIRE(!zr || (part_r && gamma_r && beta_r && stats_out_r), TS_ERR_INVALID, "ts_bn_apply_fused: residual operands");
+  TS_REQUIRE(B > 0 && C > 0 && C <= 65535 && T > 0 && pitch >= T && pitch % 8 == 0 && NB > 0 && slots > 0, TS_ERR_INVALID,
+             "ts_bn_apply_fused: bad sizes");
+  TS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), TS_ERR_INVALID, "ts_bn_apply_fused: running stats");
+  train::BnSide m{(const __nv_bfloat16*)z, part, NB, slots, gamma, beta, running_mean, running_var, stats_out, eps, momentum};
+  train::BnSide r{(const __nv_bfloat16*)zr, part_r, NB_r, slots_r, gamma_r, beta_r, running_mean_r, running_var_r,
+                  stats_out_r, eps, momentum};
+  // grid.y: split a channel only when it is long (>= 16 vectors per thread and CTA)
+  const int ny = std::max(1, std::min(64, (B * (pitch / 8)) / (256 * 16)));
+  dim3 grid(C, ny);
+  TS_CUDA(launch_pdl(train::bn_apply_fused_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0, m, r,
+                     zr != nullptr ? 1 : 0, B, C, T, pitch, (double)B * (double)T, lens, relu, (__nv_bfloat16*)y));
+  TS_LAUNCH_CHECK("bn_apply_fused_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_apply_fused(const void* dy, const void* z, const float* gamma, const float* stats, float* dgamma,
+                                     float* dbeta, void* dz, const void* zr, const float* gamma_r, const float* stats_r,
+                                     float* dgamma_r, float* dbeta_r, void* dzr, const float* sums, int B, int C, int T,
+                                     int pitch, int relu, void* stream) {
+  TS_REQUIRE(dy && z && gamma && stats && dgamma && dbeta && dz && sums, TS_ERR_INVALID, "ts_bn_bwd_apply_fused: null pointer");
+  TS_REQUIRE(!zr || (gamma_r && stats_r && dgamma_r && dbeta_r && dzr), TS_ERR_INVALID, "ts_bn_bwd_apply_fused: residual operands");
+  TS_REQUIRE(B > 0 && C > 0 && C <= 65535 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID,
+             "ts_bn_bwd_apply_fused: bad sizes");
+  train::BnBwdSide m{(const __nv_bfloat16*)z, gamma, stats, dgamma, dbeta, (__nv_bfloat16*)dz};
+  train::BnBwdSide r{(const __nv_bfloat16*)zr, gamma_r, stats_r, dgamma_r, dbeta_r, (__nv_bfloat16*)dzr};
+  const int ny = std::max(1, std::min(64, (B * (pitch / 8)) / (256 * 16)));
+  dim3 grid(C, ny);
+  TS_CUDA(launch_pdl(train::bn_bwd_apply_fused_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     (const __nv_bfloat16*)dy, m, r, zr != nullptr ? 1 : 0, sums, B, C, T, pitch, (double)B * (double)T, relu));
+  TS_LAUNCH_CHECK("bn_bwd_apply_fused_kernel");
+  return TS_OK;
+}
 
 extern "C" int ts_prep_weights(const long long* table, int n_entries, long long total_tiles, void* stream) {
   TS_REQUIRE(table != nullptr && n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), TS_ERR_INVALID,

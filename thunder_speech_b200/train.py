@@ -122,6 +122,48 @@ def ctc_loss(logits: Tensor, T: int, in_len: Tensor, targets: Tensor, tgt_len: T
     return loss, grad
 
 
+def bn_apply_fused(z: Tensor, part: Tensor, bn: nn.BatchNorm1d, zr: Optional[Tensor], part_r: Optional[Tensor],
+                   rbn: Optional[nn.BatchNorm1d], T: int, lens: Optional[Tensor], relu: bool, update_running: bool):
+    """y = act(BN(z) [+ BN_r(zr)]) with batch statistics taken from the partial sums ``part`` [NB, C, slots, 2]; returns
+    (y, stats [4, C], stats_r): stats = (scale, shift, mean, inv) for the backward pass.  Running statistics are updated in
+    place like nn.BatchNorm1d(momentum) does in train() (unbiased variance for the running estimate)."""
+    B, C, pitch = z.shape
+    y = torch.empty_like(z)
+    stats = torch.empty((4, C), device=z.device, dtype=torch.float32)
+    stats_r = torch.empty((4, C), device=z.device, dtype=torch.float32) if zr is not None else None
+
+    def run_ptrs(b):
+        upd = update_running and b.track_running_stats
+        return (_p(b.running_mean) if upd else None, _p(b.running_var) if upd else None)
+
+    rm, rv = run_ptrs(bn)
+    rmr, rvr = run_ptrs(rbn) if rbn is not None else (None, None)
+    mom = bn.momentum if bn.momentum is not None else BN_MOMENTUM
+    with ops._timed("bn_apply", bytes=B * C * T * 2 * (3 if zr is not None else 2), flops=0):
+        _lib.check(_lib.lib().ts_bn_apply_fused(
+            _p(z), _p(part), part.shape[0], part.shape[2], _p(bn.weight), _p(bn.bias), rm, rv, _p(stats),
+            _p(zr), _p(part_r), part_r.shape[0] if part_r is not None else 0, part_r.shape[2] if part_r is not None else 0,
+            _p(rbn.weight) if rbn is not None else None, _p(rbn.bias) if rbn is not None else None, rmr, rvr, _p(stats_r),
+            float(bn.eps), float(mom), B, C, T, pitch, _p(lens), int(relu), _p(y), _stream()), "ts_bn_apply_fused")
+    return y, stats, stats_r
+
+
+def bn_bwd_apply_fused(dy: Tensor, z: Tensor, bn: nn.BatchNorm1d, stats: Tensor, zr: Optional[Tensor],
+                       rbn: Optional[nn.BatchNorm1d], stats_r: Optional[Tensor], sums: Tensor, T: int, relu: bool = True):
+    """(dz, dzr) of BatchNorm + ReLU from the partial sums of bn_bwd_reduce; dgamma / dbeta go straight into the
+    parameters' gradient buffers."""
+    B, C, pitch = z.shape
+    dz = torch.empty_like(z)
+    dzr = torch.empty_like(z) if zr is not None else None
+    with ops._timed("bn_bwd_apply", bytes=B * C * T * 2 * (6 if zr is not None else 4), flops=0):
+        _lib.check(_lib.lib().ts_bn_bwd_apply_fused(
+            _p(dy), _p(z), _p(bn.weight), _p(stats), _p(_grad(bn.weight)), _p(_grad(bn.bias)), _p(dz), _p(zr),
+            _p(rbn.weight) if rbn is not None else None, _p(stats_r),
+            _p(_grad(rbn.weight)) if rbn is not None else None, _p(_grad(rbn.bias)) if rbn is not None else None, _p(dzr),
+            _p(sums), B, C, T, pitch, int(relu), _stream()), "ts_bn_bwd_apply_fused")
+    return dz, dzr
+
+
 def bn_apply(z, scale, shift, zr, scale_r, shift_r, T, lens, relu=True) -> Tensor:
     B, C, pitch = z.shape
     y = torch.empty_like(z)
@@ -373,19 +415,18 @@ class BlockTrainer:
             wpw = self.pack.get(sb.pw.weight)[0]
             z, zst = pw_gemm_stats(wpw, a, Ta)
             nn_ = B * Ta
-            scale, shift, mean, inv = bn_finalize(zst, nn_, sb.bn, update_running)
-            rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, mean=mean, inv=inv, n=nn_,
-                       mask=(scale, shift, None, None))
+            rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, n=nn_)
             if last and self.res is not None:
                 rconv, rbn = self.res
                 wr = self.pack.get(rconv.weight)[0]
                 zr, zrst = pw_gemm_stats(wr, x, T)
-                scale_r, shift_r, mean_r, inv_r = bn_finalize(zrst, B * T, rbn, update_running)
-                y = bn_apply(z, scale, shift, zr, scale_r, shift_r, Ta, la if zero_tail else None, True)
-                rec.update(zr=zr, mean_r=mean_r, inv_r=inv_r, mask=(scale, shift, scale_r, shift_r))
+                y, st, st_r = bn_apply_fused(z, zst, sb.bn, zr, zrst, rbn, Ta, la if zero_tail else None, True,
+                                             update_running)
+                rec.update(zr=zr, stats=st, stats_r=st_r)
             else:
                 tail = la if (not last or zero_tail) else None
-                y = bn_apply(z, scale, shift, None, None, None, Ta, tail, True)
+                y, st, _ = bn_apply_fused(z, zst, sb.bn, None, None, None, Ta, tail, True, update_running)
+                rec.update(stats=st)
             rec["y"] = y
             tape["subs"].append(rec)
             cur, Tc, lc = y, Ta, la
@@ -412,15 +453,12 @@ class BlockTrainer:
             has_res = last and self.res is not None
             Ta = rec["Ta"]
             # the ReLU mask is rebuilt from z with the forward scale / shift (y is not read again)
-            sums = bn_bwd_reduce(g, None, rec["z"], rec.get("zr") if has_res else None, Ta, True, partial=True,
-                                 mask=rec["mask"])
-            coef = bn_bwd_coef(sums, 1, rec["n"], sb.bn, rec["mean"], rec["inv"])
-            coef_r = None
-            if has_res:
-                rconv, rbn = self.res
-                coef_r = bn_bwd_coef(sums, 2, rec["n"], rbn, rec["mean_r"], rec["inv_r"])
-            dz, dzr = bn_bwd_apply(g, None, rec["z"], rec.get("zr") if has_res else None, coef, coef_r, Ta, True,
-                                   mask=rec["mask"])
+            st, st_r = rec["stats"], rec.get("stats_r")
+            zr = rec.get("zr") if has_res else None
+            sums = bn_bwd_reduce(g, None, rec["z"], zr, Ta, True, partial=True,
+                                 mask=(st[0], st[1], st_r[0] if has_res else None, st_r[1] if has_res else None))
+            dz, dzr = bn_bwd_apply_fused(g, rec["z"], sb.bn, st, zr, self.res[1] if has_res else None,
+                                         st_r if has_res else None, sums, Ta, True)
             # pointwise conv: weight gradient on the tensor cores, input gradient = W^T dz (masked like `a` was)
             side.run(lambda dz=dz, rec=rec, sb=sb, Ta=Ta: pw_wgrad(dz, rec["a"], Ta, out=_grad(sb.pw.weight)), dz)
             first = r == 0
