@@ -35,7 +35,7 @@ __device__ __forceinline__ float lse2(float a, float b) {
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(fmaxf(a, b), c);
   if (m == NEG_INF) return NEG_INF;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));   // sum in [1, 3]: absolute error of __logf ~2^-21
 }
 
 __global__ void __launch_bounds__(2 * ROLE_THREADS)
@@ -130,7 +130,8 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, int V, int T, int pitch,
         out[(size_t)t * Sp + s] = v;
       }
     }
-    __syncthreads();
+    // the two recursions are independent: each role synchronises on its own named barrier (ids 1 and 2)
+    asm volatile("bar.sync %0, %1;" ::"r"(role + 1), "r"(ROLE_THREADS) : "memory");
   }
   if (tid == 0) {
     const float* last = st + ((len - 1) & 1) * (Sp + 4) + 2;   // alpha buffer of the final step
