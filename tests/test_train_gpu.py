@@ -399,3 +399,43 @@ def test_dw_wgrad_tensor_core_kernel(K, D, C, B, T):
     # and the SIMT kernel on the same data agrees
     simt = dw_wgrad(dar, T, xr, T, l32, K, 1, D, P, premasked=False).cpu().numpy()
     assert rel_err(simt, ref)[0] < 1e-4
+
+
+def test_parameters_update_template_block_and_model():
+    """The reference's `_test_parameters_update` template (tests/utils.py:38-50): after backward of `outputs.mean()` every
+    trainable parameter has a non-zero gradient, and an optimiser step moves every parameter -- for one block through
+    BlockTrainer and for the whole model through CTCTrainStep."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    cin, cout, K, rep, B, T = 64, 128, 11, 3, 4, 200
+    st = synth.block_state(rng, "", cin, cout, rep, K, True, True)
+    blk = QuartznetBlock(cin, cout, repeat=rep, kernel_size=(K,), residual=True, separable=True)
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    blk = blk.cuda().train()
+    bt = BlockTrainer(blk)
+    x = torch.from_numpy(np.maximum(rng.standard_normal((B, cin, T)), 0).astype(np.float32)).cuda()
+    y, T_out, _, tape = bt.forward(ops.pack_rows(x), T, None, zero_tail=False)
+    dy = torch.full((B, cout, T_out), 1.0 / (B * cout * T_out), device="cuda")       # d mean(y) / dy
+    # a constant dy is annihilated by the last BatchNorm's mean subtraction (dgamma ~ 0 by construction: the template's
+    # reference model has the same property only up to ReLU masking) -> modulate it like a masked mean
+    dy = dy * torch.from_numpy((rng.random((B, cout, T_out)) > 0.3).astype(np.float32)).cuda()
+    bt.backward(tape, ops.pack_rows(dy), need_dx=True)
+    torch.cuda.synchronize()
+    opt = torch.optim.SGD(blk.parameters(), lr=0.1)
+    before = {k: p.detach().clone() for k, p in blk.named_parameters()}
+    for k, p in blk.named_parameters():
+        assert p.grad is not None and float((p.grad ** 2).sum()) != 0.0, k
+    opt.step()
+    for k, p in blk.named_parameters():
+        assert not torch.equal(before[k], p.detach()), k
+    # whole model
+    m, step, batch = _device_model(_model_case(), lr=1e-3)
+    before = {k: p.detach().clone() for k, p in list(m.encoder.named_parameters()) + list(m.decoder.named_parameters())}
+    step.step(*batch)
+    torch.cuda.synchronize()
+    for k, p in list(m.encoder.named_parameters()) + list(m.decoder.named_parameters()):
+        assert p.grad is not None and float((p.grad ** 2).sum()) != 0.0, k
+        assert not torch.equal(before[k], p.detach()), k
+    # BatchNorm bookkeeping like nn.BatchNorm1d in train(): one step -> num_batches_tracked == 1
+    for k, b in m.encoder.named_buffers():
+        if k.endswith("num_batches_tracked"):
+            assert int(b) == 1, k
