@@ -234,3 +234,34 @@ def test_sharded_predict_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_vectorised_detokenisation_equals_reference_rules():
+    """`_finish` (code-point table / object-array join) == the reference's per-token join + replacements + special-token
+    removal (text_processing/transform.py:93-122, vocab.py:85-130) on random id rows, for a character vocabulary with
+    all special tokens, a word-piece vocabulary, and a vocabulary whose ordinary tokens spell a special token."""
+    rng = np.random.default_rng(5)
+
+    def slow(tt, row):
+        out = "".join(tt.vocab.itos[int(i)] for i in row)
+        out = out.replace("▁", " ").replace("|", " ")
+        return tt.vocab.remove_special_tokens(out)
+
+    cases = [
+        BatchTextTransformer(synth.quartznet_vocab(), pad_token="<pad>", unknown_token="<unk>", start_token="<bos>",
+                             end_token="<eos>"),
+        BatchTextTransformer(synth.citrinet_vocab(256)),
+        BatchTextTransformer(["<", "b", "l", "a", "n", "k", ">", "|", "▁", "é", "字"]),   # "<blank>" can be spelled
+    ]
+    for tt in cases:
+        V = len(tt.vocab.itos)
+        for _ in range(50):
+            row = rng.integers(0, V, rng.integers(0, 60))
+            assert tt._finish(row) == slow(tt, row)
+        spelled = [tt.vocab.stoi[c] for c in "<blank>" if c in tt.vocab.stoi]
+        if len(spelled) == 7:
+            assert tt._finish(np.array(spelled + [tt.vocab.stoi["a"]])) == "a"      # removed as a substring, like the reference
+    col = torch.from_numpy(rng.integers(0, 29, (4, 12)).astype(np.int64))
+    cnt = torch.tensor([12, 0, 5, 1], dtype=torch.int32)
+    tt = BatchTextTransformer(synth.quartznet_vocab())
+    assert tt.decode_collapsed(col, cnt) == [slow(tt, col[b, :cnt[b]].numpy()) for b in range(4)]
