@@ -35,6 +35,7 @@ extern "C" {
 /* dtype tags for `void*` tensors */
 #define TS_F32 0
 #define TS_BF16 1
+#define TS_I16 2   /* int16 PCM (ts_pcm_ingest only) */
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* ts_version(void);
@@ -143,6 +144,24 @@ int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, v
 int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D, int P, void* stream);
 int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream);
 int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* stream);
+
+/* ---- audio ingest before the path ---------------------------------------------------------- */
+/* Reference: AudioFileLoader.preprocess_audio (src/thunder/data/dataset.py:50-77) -- mono mix, DC removal, resample
+ * (torchaudio.functional.resample) -- applied to a padded batch on the device.
+ * ts_pcm_ingest: pcm is int16 (TS_I16, scaled by 1/32768 like torchaudio.load) or float32 (TS_F32), laid out
+ * [B, channels, N] (interleaved = 0) or [B, N, channels] (interleaved = 1, the wav frame order); lens[b] (nullable) =
+ * valid samples.  out[b, n] = mean_c pcm - (remove_dc ? mean over n < lens[b] : 0) for n < lens[b], 0 up to out_pitch.
+ * scratch: >= B * ceil(N / 65536) doubles. */
+int ts_pcm_ingest(const void* pcm, int dtype, int B, int channels, int N, const int32_t* lens, int interleaved,
+                  int remove_dc, float* out, int out_pitch, double* scratch, long long scratch_doubles, void* stream);
+/* ts_resample: y[b, f * new_p + p] = sum_k taps[p][k] * x[b, f * orig_p + k - width] with x zero outside [0, len_in[b]),
+ * for f * new_p + p < ceil(new_p * len_in[b] / orig_p), zero beyond (up to out_pitch).  orig_p / new_p are the rates divided
+ * by their gcd; taps = torchaudio's _get_sinc_resample_kernel (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99),
+ * passed COMPRESSED: k0[p] = first tap of phase p that can be non-zero, taps_c [nt][new_p] with
+ * taps_c[i][p] = taps[p][k0[p] + i] (zero padded) -- the window is exactly 0 outside +-6 zero crossings. */
+int ts_resample(const float* x, int B, int N_in, int in_pitch, const int32_t* len_in, int orig_p, int new_p,
+                const float* taps_c, const int32_t* k0, int nt, int width, float* out, int N_out, int out_pitch,
+                void* stream);
 
 /* ---- training step: train()-mode BatchNorm and the backward pass ------------------------- */
 /* Reference: BaseCTCModule.training_step (src/thunder/module.py:102-127) through train()-mode QuartznetBlock

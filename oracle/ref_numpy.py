@@ -460,3 +460,57 @@ def predict(audio: np.ndarray, cfgs: List[BlockCfg], enc_state, dec_w, dec_b, vo
         return texts, dict(features=feats, feature_lengths=flen, encoded=enc, out_lengths=elen,
                            logits=logits, ids=ids)
     return texts
+
+
+# ------------------------------------------------------------------------------------------------ audio ingest
+# AudioFileLoader.preprocess_audio (src/thunder/data/dataset.py:50-77): mono mix, DC removal,
+# resample.  The resampler is torchaudio.functional.resample (torchaudio ^0.12, locked 0.12.0; not under /root/reference):
+# windowed-sinc polyphase FIR, sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99 -- restated from its published
+# algorithm (torchaudio/functional/functional.py: _get_sinc_resample_kernel / _apply_sinc_resample_kernel) and pinned
+# against tests/golden/ingest.npz, which the reference's own module produced.
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """(kernel [new', taps] float32, width, orig', new') with orig' = orig/gcd, new' = new/gcd, taps = 2*width + orig'."""
+    import math
+
+    g = math.gcd(int(orig_freq), int(new_freq))
+    o, n = int(orig_freq) // g, int(new_freq) // g
+    base = min(o, n) * rolloff
+    width = math.ceil(lowpass_filter_width * o / base)
+    idx = np.arange(-width, width + o, dtype=np.float64)[None, :] / o
+    t = (np.arange(0, -n, -1, dtype=np.float64)[:, None] / n + idx) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    k = k * window * (base / o)
+    return k.astype(np.float32), width, o, n
+
+
+def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """x [..., length] -> [..., ceil(new' * length / orig')]; float64 accumulation of the float32 taps."""
+    if int(orig_freq) == int(new_freq):
+        return np.asarray(x, np.float32)
+    k, width, o, n = sinc_resample_kernel(orig_freq, new_freq)
+    x = np.asarray(x, np.float32)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]).astype(np.float64)
+    length = x2.shape[1]
+    xp = np.pad(x2, ((0, 0), (width, width + o)))
+    nfr = (xp.shape[1] - k.shape[1]) // o + 1
+    frames = np.lib.stride_tricks.sliding_window_view(xp, k.shape[1], axis=1)[:, ::o][:, :nfr]      # [R, nfr, taps]
+    y = np.einsum("rft,pt->rfp", frames, k.astype(np.float64)).reshape(x2.shape[0], -1)              # interleave phases
+    target = -((-n * length) // o)                                                                  # ceil(n*length/o)
+    return y[:, :target].astype(np.float32).reshape(lead + (target,))
+
+
+def preprocess_audio(audio: np.ndarray, sample_rate: int, force_mono: bool = True, target_rate: int = 16000) -> np.ndarray:
+    """audio [channels, time] float -> [1 (or channels), time'] (dataset.py:50-77)."""
+    a = np.asarray(audio, np.float32).astype(np.float64)
+    if force_mono and a.shape[0] > 1:
+        a = a.mean(0, keepdims=True)
+    if a.shape[0] != 1:
+        raise RuntimeError("audio - audio.mean(1) only broadcasts for one channel (dataset.py:69)")
+    a = (a - a.mean(1)).astype(np.float32)
+    return resample(a, sample_rate, target_rate) if int(sample_rate) != int(target_rate) else a

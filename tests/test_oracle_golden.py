@@ -249,3 +249,21 @@ def test_torch_port_training_model_matches_reference():
         # random projection of the gradient: two fp32 evaluations of a 25-layer train-mode BN stack agree only to a few 1e-2 of
         # the gradient norm on the earliest layers (block-level gradients above are pinned to 2e-4)
         assert abs(float((gr * r).sum()) - proj) <= 1e-1 * norm + 1e-6, k
+
+
+def test_ingest_oracle_vs_reference_goldens():
+    """oracle.ref_numpy.preprocess_audio (mono mix, DC removal, torchaudio-style sinc resample) against outputs of the
+    reference's own AudioFileLoader.preprocess_audio (tests/golden/ingest.npz, oracle/make_golden_ingest.py)."""
+    from oracle.make_golden_ingest import CASES, clip
+
+    g = np.load("tests/golden/ingest.npz")
+    for name, ch, sr, secs in CASES:
+        pcm = clip(name, ch, sr, secs)
+        y = R.preprocess_audio(pcm.astype(np.float32) / 32768.0, sr)
+        ref = g[f"{name}.out"]
+        assert y.shape == ref.shape, name
+        assert np.abs(y - ref).max() <= 5e-5 * np.abs(ref).max(), (name, np.abs(y - ref).max() / np.abs(ref).max())
+    k, width, o, n = R.sinc_resample_kernel(44100, 16000)
+    assert (o, n, width, k.shape) == (441, 160, 17, (160, 475))
+    with pytest.raises(RuntimeError):
+        R.preprocess_audio(np.zeros((2, 100), np.float32), 16000, force_mono=False)

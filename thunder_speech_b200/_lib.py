@@ -19,6 +19,7 @@ TS_ERR_UNSUPPORTED = -2
 TS_ERR_NO_DEVICE = -3
 TS_F32 = 0
 TS_BF16 = 1
+TS_I16 = 2
 TS_DW_INPUT_PREMASKED = 1
 
 _lib = None
@@ -55,6 +56,10 @@ SIGNATURES = {
     "ts_pw_wgrad_reduce": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "ts_dw_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ts_pcm_ingest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                              c_longlong, c_void_p]),
+    "ts_resample": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                            c_void_p, c_int, c_int, c_void_p]),
     "ts_prep_weights": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
     "ts_pw_gemm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p]),
