@@ -42,7 +42,6 @@ struct Params {
   CUtensorMap x, da;   // (64 frames, W windows, C, B), box (64, R, 1, NB)
   int B, C, K, P, D;
   int R, NB, HL, NQ, ACC, rows, groups;
-  int mode;            // experiment switch (option pw_bn): bit 0 = skip the MMAs (TMA pipeline only)
   float* out;          // [C, K]
 };
 
@@ -137,7 +136,7 @@ dw_wgrad_mma_kernel(const __grid_constant__ Params p) {
         ptx::tc_fence_after();
         const uint32_t sx = ptx::smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sd = sx + XS_BYTES;
-        for (int ks = 0; ks < ((p.mode & 1) ? (g == 0 ? 1 : 0) : ksteps); ++ks) {
+        for (int ks = 0; ks < ksteps; ++ks) {
           // rows ks*16 .. +15 are the K slice.  A: da rows (second M chunk = the same rows again, LBO 0 rows apart is
           // expressed as one full operand further: any finite data would do, those lanes are never read).
           const uint64_t da_ = ptx::umma_desc(sd + ks * 2048, 0, 1024);
@@ -241,7 +240,6 @@ int launch_dw_wgrad_mma(const __nv_bfloat16* da, int pitch_out, const __nv_bfloa
   p.rows = p.NB * p.R;
   p.groups = ceil_div(B, p.NB);
   p.out = out;
-  p.mode = option_pw_bn();
   int rc;
   cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[3] = {128, (cuuint64_t)pitch_in * 2, (cuuint64_t)C * pitch_in * 2};

@@ -26,7 +26,3 @@ for R in (8,):
 run(512, 87, 2, 8)
 for (C, K, D) in [(256, 33, 1), (512, 75, 1), (512, 87, 2)]:
     run(C, K, D, B, flags=1)
-_lib.set_option("pw_bn", 1)
-print("-- MMAs skipped (TMA pipeline only)")
-for (C, K, D) in [(256, 33, 1), (512, 75, 1), (512, 87, 2)]:
-    run(C, K, D, B, flags=1)
