@@ -27,6 +27,10 @@ static std::atomic<int> g_opt_pw_pair{2};
 int option_pw_pair() { return g_opt_pw_pair.load(std::memory_order_relaxed); }
 int option_pw_bn() { return g_opt_pw_bn.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_dw_base_offset{0};
+static std::atomic<int> g_opt_dw_share_halo{1};
+static std::atomic<int> g_opt_dw_pro{30};
+int option_dw_pro() { return g_opt_dw_pro.load(std::memory_order_relaxed); }
+int option_dw_share_halo() { return g_opt_dw_share_halo.load(std::memory_order_relaxed); }
 int option_dw_tma() { return g_opt_dw_tma.load(std::memory_order_relaxed); }
 int option_dw_base_offset() { return g_opt_dw_base_offset.load(std::memory_order_relaxed); }
 int option_dw_mma() { return g_opt_dw_mma.load(std::memory_order_relaxed); }
@@ -62,6 +66,14 @@ extern "C" int ts_set_option(const char* name, int value) {
   }
   if (name != nullptr && strcmp(name, "dw_base_offset") == 0) {
     ts::g_opt_dw_base_offset.store(value);
+    return TS_OK;
+  }
+  if (name != nullptr && strcmp(name, "dw_pro") == 0) {
+    ts::g_opt_dw_pro.store(value);
+    return TS_OK;
+  }
+  if (name != nullptr && strcmp(name, "dw_share_halo") == 0) {
+    ts::g_opt_dw_share_halo.store(value);
     return TS_OK;
   }
   if (name != nullptr && strcmp(name, "pw_big") == 0) {
