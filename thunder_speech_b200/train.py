@@ -279,6 +279,11 @@ class WeightPack:
     table stays valid."""
 
     def __init__(self, entries: List[Tuple[str, nn.Parameter]]):
+        self.entries = list(entries)
+        self._build()
+
+    def _build(self) -> None:
+        entries = self.entries
         self.views: Dict[int, Tuple[Tensor, Tensor]] = {}
         rows_tab = []
         tiles = 0
@@ -306,8 +311,14 @@ class WeightPack:
             self.views[id(p)] = (w, wT)
         self.n, self.tiles = len(rows_tab), tiles
         self.table = torch.tensor(rows_tab, dtype=torch.int64).to(entries[0][1].device)
+        self._src_ptrs = [p.data_ptr() for _, p in entries]
 
     def refresh(self) -> None:
+        # the table holds raw device pointers: rebuild it if a parameter's storage moved (module.to(...), re-assignment)
+        if any(p.data_ptr() != q for (_, p), q in zip(self.entries, self._src_ptrs)):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("WeightPack: a parameter was re-allocated while a CUDA graph is being captured")
+            self._build()
         _lib.check(_lib.lib().ts_prep_weights(_p(self.table), self.n, self.tiles, _stream()), "ts_prep_weights")
 
     def get(self, p: nn.Parameter) -> Tuple[Tensor, Tensor]:
@@ -614,6 +625,10 @@ class CTCTrainStep:
         """Mean CTC loss (device scalar); parameter gradients are left in ``param.grad``."""
         if not self.use_graph:
             return self._forward_backward(audio, lengths, y, y_lengths)
+        ptrs = tuple(p.data_ptr() for p in self.params)
+        if ptrs != getattr(self, "_captured_ptrs", ptrs):
+            self._graphs.clear()          # parameters were re-allocated: the captured graphs point at stale storage
+        self._captured_ptrs = ptrs
         key = (tuple(audio.shape), tuple(y.shape))
         g = self._graphs.get(key)
         if g is None:
