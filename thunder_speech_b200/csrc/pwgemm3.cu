@@ -21,7 +21,7 @@ constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;   // tile of the CTA PAI
 constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 weight rows: 16 KB
 constexpr int B_BYTES = BK * (BN / 2) * 2;     // this CTA's half of the activation tile: 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGES = 5;
+constexpr int STAGES = 6;
 constexpr int ACC = 2;
 constexpr int EPI_WARPS = 8;
 constexpr int STG_BYTES = 32 * 128;
