@@ -150,3 +150,29 @@ def test_predict_stream_matches_predict():
     want = [m.predict(x.cuda()) for x in xs]
     got = list(m.predict_stream(xs))
     assert got == want
+
+
+def test_to_torchscript_trace_roundtrip(tmp_path):
+    """`CTCModule.to_torchscript` (trace over the thunder_b200 custom ops): bit-identical logits, save / load, another batch
+    size of the same audio length (the reference exports through Lightning's to_torchscript, module.py:88 @jit.export)."""
+    import torch
+
+    from thunder_speech_b200 import synth
+    from thunder_speech_b200.runner import build_model
+
+    m = build_model("quartznet5x5", torch.device("cuda"), seed=5)
+    x = torch.from_numpy(synth.audio(2, 16000, 3, "tones")).cuda()
+    lens = torch.tensor([16000, 12000], device="cuda")
+    ref, rl = m(x, lens)
+    path = str(tmp_path / "qn5x5.pt")
+    ts = m.to_torchscript(x, lens, file_path=path)
+    out, ol = ts(x, lens)
+    assert torch.equal(out, ref) and torch.equal(ol, rl)
+    kinds = {n.kind() for n in ts.graph.nodes()}
+    assert {"thunder_b200::filterbank", "thunder_b200::dw_conv", "thunder_b200::pw_gemm"} <= kinds
+    loaded = torch.jit.load(path)
+    x3 = torch.from_numpy(synth.audio(3, 16000, 4, "tones")).cuda()
+    l3 = torch.tensor([16000, 16000, 8000], device="cuda")
+    o3, _ = loaded(x3, l3)
+    r3, _ = m(x3, l3)
+    assert torch.equal(o3, r3)

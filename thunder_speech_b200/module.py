@@ -96,6 +96,28 @@ class CTCModule(nn.Module):
         return self.text_transform.decode_collapsed(col, cnt)
 
     @torch.no_grad()
+    def to_torchscript(self, example_audio: Tensor, example_lengths: Optional[Tensor] = None,
+                       file_path: Optional[str] = None) -> "torch.jit.ScriptModule":
+        """TorchScript export of ``forward`` (audio, lengths) -> (logits, lengths), the counterpart of Lightning's
+        ``to_torchscript`` the reference relies on.  It is produced by TRACING: the graph is a sequence of
+        ``torch.ops.thunder_b200.*`` calls, runs any batch size, but is specialised to the audio LENGTH of the example (frame
+        counts are Python ints at trace time).  ``torch.jit.script`` is not offered -- the reference's own front-end does not
+        script on torch 2.x either.  Loading in a fresh process needs ``import thunder_speech_b200.ops``
+        first so that the custom ops are registered."""
+        import warnings
+
+        if example_lengths is None:
+            example_lengths = torch.full((example_audio.shape[0],), example_audio.shape[-1], device=example_audio.device)
+        was_training = self.training
+        self.eval()
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            traced = torch.jit.trace(self, (example_audio, example_lengths), check_trace=False)
+        self.train(was_training)
+        if file_path is not None:
+            torch.jit.save(traced, file_path)
+        return traced
+
     def predict_stream(self, batches: Iterable[Tensor]) -> Iterator[List[str]]:
         """Serving loop over HOST batches ``[B, N]`` of one fixed shape (pinned memory for true overlap): the
         host-to-device copy of batch i+1 runs on a copy stream while batch i computes (CUDA-graph replay), and the
