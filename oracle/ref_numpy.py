@@ -23,7 +23,7 @@ All citations are ``file:line`` relative to ``/root/reference``.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 

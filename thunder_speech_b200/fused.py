@@ -25,7 +25,7 @@ import torch
 from torch import Tensor, nn
 
 from . import ops
-from .blocks import conv_out_length, get_same_padding
+from .blocks import conv_out_length
 
 BN_EPS_DEFAULT = 1e-3
 

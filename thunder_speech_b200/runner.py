@@ -14,7 +14,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from . import _lib, ops, synth
+from . import ops, synth
 from .blocks import conv1d_decoder
 from .citrinet.blocks import CitrinetEncoder
 from .module import CTCModule

@@ -10,7 +10,6 @@ from __future__ import annotations
 from typing import List, Optional
 
 import numpy as np
-import torch
 from torch import Tensor, nn
 
 __all__ = ["Vocabulary", "BatchTextTransformer"]
