@@ -211,6 +211,10 @@ assert flat.numel() == 8 and lin.weight.grad.data_ptr() == flat.data_ptr()
 lin.weight.grad.fill_(1.0 + dist.get_rank()); lin.bias.grad.fill_(10.0 * dist.get_rank())
 allreduce_mean_(flat)
 assert torch.allclose(lin.weight.grad, torch.full((2, 3), 1.5)) and torch.allclose(lin.bias.grad, torch.full((2,), 5.0))
+from thunder_speech_b200.parallel import ensure_grad_views
+assert not ensure_grad_views(list(lin.parameters()), flat)
+lin.bias.grad = None                        # what optimizer.zero_grad(set_to_none=True) does
+assert ensure_grad_views(list(lin.parameters()), flat) and lin.bias.grad.data_ptr() == flat.data_ptr() + 6 * 4
 out = sharded_predict(fake_predict, audio)
 assert out == ["utt%d" % i for i in range(7)], out
 lo, hi = shard_bounds(7, 2, dist.get_rank())

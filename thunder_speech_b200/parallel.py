@@ -51,6 +51,20 @@ def flat_grad_views(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
     return flat
 
 
+def ensure_grad_views(params: Sequence[torch.nn.Parameter], flat: torch.Tensor) -> bool:
+    """Re-points every ``param.grad`` at its slice of `flat` if user code replaced it (``zero_grad(set_to_none=True)``,
+    ``param.grad = ...``).  Returns True when something had to be repaired."""
+    off, repaired = 0, False
+    for p in params:
+        n = p.numel()
+        g = p.grad
+        if g is None or g.data_ptr() != flat.data_ptr() + off * flat.element_size() or g.shape != p.shape:
+            p.grad = flat[off:off + n].view_as(p)
+            repaired = True
+        off += n
+    return repaired
+
+
 def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
     """In-place mean of `flat` over all ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests); no-op when
     torch.distributed is not initialised or world_size == 1.  This is what DDP does for the reference's training_step."""

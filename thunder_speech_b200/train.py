@@ -25,7 +25,7 @@ from torch import Tensor, nn
 
 from . import _lib, ops
 from .blocks import conv_out_length
-from .parallel import allreduce_mean_, flat_grad_views
+from .parallel import allreduce_mean_, ensure_grad_views, flat_grad_views
 
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.1
@@ -625,6 +625,8 @@ class CTCTrainStep:
         """Mean CTC loss (device scalar); parameter gradients are left in ``param.grad``."""
         if not self.use_graph:
             return self._forward_backward(audio, lengths, y, y_lengths)
+        if ensure_grad_views(self.params, self.flat):
+            self._graphs.clear()          # the captured graphs wrote into gradient tensors that are no longer attached
         ptrs = tuple(p.data_ptr() for p in self.params)
         if ptrs != getattr(self, "_captured_ptrs", ptrs):
             self._graphs.clear()          # parameters were re-allocated: the captured graphs point at stale storage
