@@ -145,6 +145,11 @@ int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D,
 int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream);
 int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* stream);
 
+/* SpecAugment / SpecCutout (src/thunder/quartznet/spec_augment.py:23-110, training only): zero IN PLACE every element
+ * (b, f, t) of feat ([B, C, pitch] f32 or bf16, valid frames < T) that lies in any of the n rectangles
+ * rects[i] = {f0, f1, t0, t1} (half-open; device memory, int32).  The same rectangles for every utterance. */
+int ts_spec_mask(void* feat, int dtype, int B, int C, int T, int pitch, const int32_t* rects, int n, void* stream);
+
 /* ---- audio ingest before the path ---------------------------------------------------------- */
 /* Reference: AudioFileLoader.preprocess_audio (src/thunder/data/dataset.py:50-77) -- mono mix, DC removal, resample
  * (torchaudio.functional.resample) -- applied to a padded batch on the device.

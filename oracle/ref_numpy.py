@@ -514,3 +514,40 @@ def preprocess_audio(audio: np.ndarray, sample_rate: int, force_mono: bool = Tru
         raise RuntimeError("audio - audio.mean(1) only broadcasts for one channel (dataset.py:69)")
     a = (a - a.mean(1)).astype(np.float32)
     return resample(a, sample_rate, target_rate) if int(sample_rate) != int(target_rate) else a
+
+
+# ------------------------------------------------------------------------------------------------ SpecAugment / SpecCutout
+# src/thunder/quartznet/spec_augment.py:23-110 (train() mode).  The mask intervals come from torch.rand(1) on the host
+# generator (torchaudio.functional.mask_along_axis / _create_mask): v = rand * param, v0 = rand * (size - v), masked
+# [long(v0), long(v0) + long(v)), the same interval for every utterance.  `draw()` must return those uniform numbers in order
+# (tests pass `lambda: float(torch.rand(1))` after torch.manual_seed to reproduce the reference's stream).
+
+def _mask_interval(size: int, param: int, draw):
+    value = np.float32(draw()) * np.float32(param)
+    min_value = np.float32(draw()) * (np.float32(size) - value)
+    start = int(min_value)
+    return start, start + int(value)
+
+
+def spec_augment(x: np.ndarray, draw, time_masks=0, freq_masks=0, time_width=10, freq_width=10) -> np.ndarray:
+    """x [B, C, T]: time masks first, then frequency masks; a mask with param < 1 is skipped (mask_along_axis)."""
+    y = np.array(x, copy=True)
+    for _ in range(time_masks):
+        if time_width >= 1:
+            a, b = _mask_interval(y.shape[2], time_width, draw)
+            y[:, :, a:b] = 0
+    for _ in range(freq_masks):
+        if freq_width >= 1:
+            a, b = _mask_interval(y.shape[1], freq_width, draw)
+            y[:, a:b, :] = 0
+    return y
+
+
+def spec_cutout(x: np.ndarray, draw, rect_masks=0, time_width=5, freq_width=20) -> np.ndarray:
+    """Rectangles; like the reference, BOTH extents are drawn with freq_width (spec_augment.py:106-107)."""
+    y = np.array(x, copy=True)
+    for _ in range(rect_masks):
+        f0, f1 = _mask_interval(y.shape[1], freq_width, draw)
+        t0, t1 = _mask_interval(y.shape[2], freq_width, draw)
+        y[:, f0:f1, t0:t1] = 0
+    return y

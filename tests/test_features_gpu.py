@@ -111,3 +111,75 @@ def test_features_bf16_padded_rows():
     emax, el2 = rel_err(got[:, :, :101], rf)
     assert emax < 2e-2 and el2 < 2e-2
     assert (got[:, :, 101:] == 0).all()
+
+
+def test_spec_augment_and_cutout_vs_reference_goldens():
+    """Device SpecAugment / SpecCutout under the reference's seeds == outputs of the reference's own modules
+    (tests/golden/augment.npz): eager mode makes the same host draws in the same order.  Also: identity in eval(), bf16 rows in
+    place, and the factory wiring (children 4.., training only)."""
+    import numpy as np
+    import torch
+
+    from oracle.make_golden_augment import CASES, case_input
+    from thunder_speech_b200 import ops, synth
+    from thunder_speech_b200.quartznet.spec_augment import SpecAugment, SpecCutout
+    from thunder_speech_b200.quartznet.transform import FilterbankFeatures
+
+    g = np.load("tests/golden/augment.npz")
+    for name, kind, kw, shape, seed in CASES:
+        x = torch.from_numpy(case_input(name, shape)).cuda()
+        layer = (SpecAugment if kind == "augment" else SpecCutout)(**kw).train()
+        torch.manual_seed(seed)
+        y = layer(x)
+        assert np.array_equal(y.cpu().numpy(), g[f"{name}.out"]), name
+        assert torch.equal(x.cpu(), torch.from_numpy(case_input(name, shape)))        # input untouched, like masked_fill
+        assert layer.eval()(x) is x
+        rows = ops.pack_rows(x)
+        torch.manual_seed(seed)
+        layer.train()(rows, T=shape[2])
+        # bf16 rows: the values are rounded, the zero pattern must be the reference's
+        assert np.array_equal(ops.unpack_rows(rows, shape[2]).cpu().numpy() == 0, g[f"{name}.out"] == 0), name
+    # factory: augmentation only in train(), features elsewhere unchanged
+    audio = torch.from_numpy(synth.audio(2, 16000, 3, "noise")).cuda()
+    lens = torch.tensor([16000, 12000], device="cuda")
+    fb = FilterbankFeatures(dither=0.0, num_time_masks=2, num_freq_masks=2, mask_time_width=30, mask_freq_width=10).cuda()
+    plain = FilterbankFeatures(dither=0.0).cuda().eval()
+    ref, _ = plain(audio, lens)
+    out_eval, _ = fb.eval()(audio, lens)
+    assert torch.equal(out_eval, ref)
+    torch.manual_seed(5)
+    out_train, _ = fb.train()(audio, lens)
+    masked = (out_train == 0) & (ref != 0)
+    assert masked.any() and torch.equal(out_train[~masked], ref[~masked])
+    cols = masked[0].all(0).nonzero().numel()
+    rowsm = masked[0][:, ~masked[0].all(0)].any(1).sum().item()
+    assert cols <= 2 * 30 and rowsm <= 2 * 10
+
+
+def test_spec_augment_under_cuda_graph_capture_uses_device_draws():
+    """While a CUDA graph is captured the mask intervals are drawn on the device: every replay masks fresh intervals that
+    respect the width limits."""
+    import torch
+
+    from thunder_speech_b200.quartznet.spec_augment import SpecAugment
+
+    layer = SpecAugment(time_masks=2, freq_masks=1, time_width=40, freq_width=12).train()
+    base = torch.full((2, 64, 256), 1.0, device="cuda")
+    work = base.clone()
+    layer(work.clone())                       # warm-up outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        work.copy_(base)
+        layer(work, T=256)                    # in place (the rows form of the call)
+    patterns = []
+    for _ in range(6):
+        g.replay()
+        torch.cuda.synchronize()
+        z = (work == 0)
+        assert torch.equal(z[0], z[1])        # same intervals for every utterance
+        tcols = z[0].all(0)
+        frows = z[0][:, ~tcols].any(1) if (~tcols).any() else torch.zeros(64, dtype=torch.bool, device="cuda")
+        assert int(tcols.sum()) <= 2 * 40 and int(frows.sum()) <= 12
+        patterns.append(z[0].cpu())
+    assert any(not torch.equal(patterns[0], p) for p in patterns[1:])

@@ -267,3 +267,19 @@ def test_ingest_oracle_vs_reference_goldens():
     assert (o, n, width, k.shape) == (441, 160, 17, (160, 475))
     with pytest.raises(RuntimeError):
         R.preprocess_audio(np.zeros((2, 100), np.float32), 16000, force_mono=False)
+
+
+def test_spec_augment_oracle_vs_reference_goldens():
+    """oracle spec_augment / spec_cutout fed with the host generator's draws == the reference's own modules under the same
+    seed (tests/golden/augment.npz, oracle/make_golden_augment.py)."""
+    import torch
+
+    from oracle.make_golden_augment import CASES, case_input
+
+    g = np.load("tests/golden/augment.npz")
+    for name, kind, kw, shape, seed in CASES:
+        x = case_input(name, shape)
+        torch.manual_seed(seed)
+        draw = lambda: float(torch.rand(1))
+        y = R.spec_augment(x, draw, **kw) if kind == "augment" else R.spec_cutout(x, draw, **kw)
+        assert np.array_equal(y, g[f"{name}.out"]), name

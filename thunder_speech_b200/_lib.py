@@ -56,6 +56,7 @@ SIGNATURES = {
     "ts_pw_wgrad_reduce": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "ts_dw_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ts_spec_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ts_pcm_ingest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_longlong, c_void_p]),
     "ts_resample": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -341,3 +341,46 @@ extern "C" int ts_se_apply(const void* y1, const float* gate, int B, int C, int 
   TS_LAUNCH_CHECK("se_apply_kernel");
   return TS_OK;
 }
+
+// ---- SpecAugment / SpecCutout (training-time feature masking, src/thunder/quartznet/spec_augment.py) ---------------
+// Zeroes, in place, every element (b, f, t) that lies inside ANY of the n rectangles [f0, f1) x [t0, t1); the same
+// rectangles for every utterance (mask_along_axis: "all examples will have the same mask interval").  The rectangles live
+// in DEVICE memory so that a CUDA-graph replay can use fresh draws.  One thread per element; only elements inside a
+// rectangle are written.
+namespace ts {
+namespace misc {
+template <typename T>
+__global__ void spec_mask_kernel(T* __restrict__ feat, int C, int Tn, int pitch, const int32_t* __restrict__ rects, int n,
+                                 long long rows) {
+  extern __shared__ int32_t sr[];
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) sr[i] = rects[i];
+  __syncthreads();
+  const long long row = blockIdx.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= rows || t >= Tn) return;
+  const int f = (int)(row % C);
+  bool hit = false;
+  for (int i = 0; i < n; ++i) hit = hit || (f >= sr[4 * i] && f < sr[4 * i + 1] && t >= sr[4 * i + 2] && t < sr[4 * i + 3]);
+  if (hit) feat[row * pitch + t] = T(0.f);
+}
+}  // namespace misc
+}  // namespace ts
+
+extern "C" int ts_spec_mask(void* feat, int dtype, int B, int C, int T, int pitch, const int32_t* rects, int n,
+                            void* stream) {
+  TS_REQUIRE(feat && (rects || n == 0), TS_ERR_INVALID, "ts_spec_mask: null pointer");
+  TS_REQUIRE(dtype == TS_F32 || dtype == TS_BF16, TS_ERR_INVALID, "ts_spec_mask: bad dtype");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && n >= 0 && n <= 1024, TS_ERR_INVALID, "ts_spec_mask: bad sizes");
+  if (n == 0) return TS_OK;
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_spec_mask: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(T, 256));
+  const size_t smem = (size_t)4 * n * sizeof(int32_t);
+  if (dtype == TS_F32)
+    misc::spec_mask_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((float*)feat, C, T, pitch, rects, n, rows);
+  else
+    misc::spec_mask_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)feat, C, T, pitch, rects,
+                                                                                      n, rows);
+  TS_LAUNCH_CHECK("spec_mask_kernel");
+  return TS_OK;
+}

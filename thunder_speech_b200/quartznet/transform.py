@@ -125,12 +125,13 @@ class _FusedFilterbank(nn.Sequential):
     """The object returned by :func:`FilterbankFeatures`.  Children ``0..3`` mirror the reference's
     ``MultiSequential`` so that indexing (``fb[1].window``) and ``state_dict`` keys are unchanged."""
 
-    def __init__(self, dither, preemph, n_window_size, n_window_stride, n_fft, sample_rate, nfilt):
+    def __init__(self, dither, preemph, n_window_size, n_window_stride, n_fft, sample_rate, nfilt, augment=()):
         super().__init__(
             Masked(DitherAudio(dither=dither), PreEmphasisFilter(preemph=preemph)),
             PowerSpectrum(n_window_size=n_window_size, n_window_stride=n_window_stride, n_fft=n_fft),
             Masked(MelScale(sample_rate=sample_rate, n_fft=n_fft, nfilt=nfilt)),
             FeatureBatchNormalizer(),
+            *[Masked(a) for a in augment],   # children 4.. like the reference factory (transform.py:299-318)
         )
         self._tables = None  # (key, dict of device tensors) derived from the buffers
 
@@ -188,10 +189,18 @@ class _FusedFilterbank(nn.Sequential):
             if self.training and dither.dither != 0:
                 audio = dither(audio)
             t = self._device_tables(audio.device)
-            return torch.ops.thunder_b200.filterbank(
+            feats, feat_len = torch.ops.thunder_b200.filterbank(
                 audio, lengths, t["window_full"], t["twiddle"], t["mel_start"], t["mel_count"], t["mel_off"],
                 t["mel_w"], ps.hop_length, float(pre.preemph), t["win_lo"], t["win_hi"], float(norm.div_guard),
                 int(bf16_pitch))
+            if self.training and len(self) > 4:   # SpecCutout / SpecAugment: in place on the fresh feature tensor
+                from .spec_augment import apply_rects
+
+                F = 1 + audio.shape[-1] // ps.hop_length
+                for child in list(self)[4:]:
+                    aug = child.layer[0]
+                    apply_rects(feats, F, aug.rects(feats.shape[1], F, feats.device))
+            return feats, feat_len
 
     def forward(self, audio: Tensor, lengths: Tensor) -> Tuple[Tensor, Tensor]:
         return self.features(audio, lengths, 0)
@@ -211,11 +220,16 @@ def FilterbankFeatures(
     mask_time_width: int = 50,
     mask_freq_width: int = 20,
 ) -> nn.Module:
-    """Same signature and error behaviour as the reference factory (transform.py:258-321).
-    SpecAugment / SpecCutout (training-only, off by default, transform.py:266-268) are outside the
-    forward hot path and not implemented."""
+    """Same signature and error behaviour as the reference factory (transform.py:258-321), including the training-time
+    SpecCutout / SpecAugment stages appended as children 4.. (identity in eval())."""
     if num_cutout_masks > 0 and (num_freq_masks + num_time_masks > 0):
         raise ValueError("Cutout and SpecAugment can't be used at the same time.")
-    if num_cutout_masks > 0 or (num_freq_masks + num_time_masks > 0):
-        raise NotImplementedError("SpecAugment/SpecCutout are out of scope of the B200 forward hot path")
-    return _FusedFilterbank(dither, preemph, n_window_size, n_window_stride, n_fft, sample_rate, nfilt)
+    from .spec_augment import SpecAugment, SpecCutout
+
+    augment = []
+    if num_cutout_masks > 0:
+        augment.append(SpecCutout(rect_masks=num_cutout_masks, time_width=mask_time_width, freq_width=mask_freq_width))
+    if num_freq_masks + num_time_masks > 0:
+        augment.append(SpecAugment(time_masks=num_time_masks, freq_masks=num_freq_masks, time_width=mask_time_width,
+                                   freq_width=mask_freq_width))
+    return _FusedFilterbank(dither, preemph, n_window_size, n_window_stride, n_fft, sample_rate, nfilt, augment)
