@@ -150,8 +150,7 @@ class TrainWorkload:
 
         self.name, self.B, self.N, self.dev = name, B, N, dev
         self.model = build_model("quartznet15x5", dev)
-        self.model.encoder.train()
-        self.model.decoder.train()
+        self.model.train()     # like the reference's training_step: dither (1e-5) in the front-end, batch-stat BatchNorm
         self.trainer = CTCTrainStep(self.model, lr=1e-4)
         rng = np.random.Generator(np.random.PCG64(99 + rank))
         self.host_audio = torch.from_numpy(synth.audio(B, N, 1234 + rank, "noise")).pin_memory()
