@@ -204,6 +204,22 @@ int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, float* out, v
 int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
                 int B, int C, int K, int S, int D, int P, int bchunk, int flags, float* part, void* stream);
 
+/* SqueezeExcite variants for Citrinet training (citrinet/blocks.py:48-83,177-197): the main branch of a block's last
+ * sub-block is u = BN(z) scaled by gate[b, c] = sigmoid(W2 relu(W1 mean_t u)) before the residual add and ReLU.
+ *   ts_bn_apply_se:      y = act(gate[b,c] * (z*scale+shift) (+ zr*scale_r+shift_r)), tail zeroed
+ *   ts_bn_bwd_reduce_se: sums [B, C, 3] like ts_bn_bwd_reduce, the ReLU mask rebuilt WITH the gate
+ *   ts_bn_bwd_apply_se:  dz = a * (dym * gate[b,c] + addc[b,c]) + b * z + c0 (addc = d loss / d mean_t(u) / T, every frame);
+ *                        dzr = a_r * dym + b_r * zr + c0_r. */
+int ts_bn_apply_se(const void* z, const float* scale, const float* shift, const void* zr, const float* scale_r,
+                   const float* shift_r, const float* gate, int B, int C, int T, int pitch, const int32_t* lens, int relu,
+                   void* y, void* stream);
+int ts_bn_bwd_reduce_se(const void* dy, const void* z, const void* zr, int B, int C, int T, int pitch, int relu, float* sums,
+                        const float* mask_scale, const float* mask_shift, const float* mask_scale_r,
+                        const float* mask_shift_r, const float* gate, void* stream);
+int ts_bn_bwd_apply_se(const void* dy, const void* z, const void* zr, const float* coef, const float* coef_r, int B, int C,
+                       int T, int pitch, int relu, void* dz, void* dzr, const float* mask_scale, const float* mask_shift,
+                       const float* mask_scale_r, const float* mask_shift_r, const float* gate, const float* addc,
+                       void* stream);
 /* Prepares every weight operand of a training step from the fp32 master weights in ONE launch.  `table` is a device array
  * of n_entries rows of 8 int64: {src, dst, dstT, rows, cols, ldT, kind, first_tile}; tiles are 32 x 32 elements and
  * first_tile is the running sum of ceil(rows/32) * ceil(cols/32).  kind 0 (pointwise / decoder weight [rows, cols] f32):

@@ -439,3 +439,60 @@ def test_parameters_update_template_block_and_model():
     for k, b in m.encoder.named_buffers():
         if k.endswith("num_batches_tracked"):
             assert int(b) == 1, k
+
+
+@pytest.mark.parametrize("cin,cout,K,rep,B,T,res", [(64, 128, 11, 3, 4, 200, True), (32, 64, 5, 1, 6, 101, False),
+                                                     (256, 256, 13, 5, 8, 251, True)])
+def test_citrinet_block_with_squeeze_excite_training(cin, cout, K, rep, B, T, res):
+    """train()-mode forward and every gradient (incl. the SqueezeExcite FCs) of a stride-1 CitrinetBlock against the autograd
+    torch port, bf16 storage simulated (citrinet/blocks.py:48-83,177-197)."""
+    from oracle import ref_torch as RT
+    from thunder_speech_b200.citrinet.blocks import CitrinetBlock
+
+    rng = np.random.Generator(np.random.PCG64(cin + K + rep))
+    st = synth.block_state(rng, "", cin, cout, rep, K, res, True, se=True)
+    x = np.maximum(rng.standard_normal((B, cin, T)), 0).astype(np.float32)
+    lens = np.sort(rng.integers(T // 2, T + 1, B))[::-1].astype(np.int64).copy()
+    lens[0] = T
+    m = (np.arange(T)[None, :] < lens[:, None])[:, None, :]
+    Rm = np.where(m, rng.standard_normal((B, cout, T)), 0).astype(np.float32)
+    cfg = R.BlockCfg(cin, cout, repeat=rep, kernel_size=K, residual=res, separable=True, kind="citrinet")
+    def oracle(store):
+        sd = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st.items()}
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and "running" not in k:
+                v.requires_grad_(True)
+        xi = torch.from_numpy(np.where(m, x, 0).astype(np.float32)).requires_grad_(True)
+        yo, _ = RT.block(xi, torch.from_numpy(lens), cfg, sd, "", train=True, store=store)
+        (yo * torch.from_numpy(Rm)).sum().backward()
+        return sd, xi.grad.numpy(), yo.detach().numpy()
+
+    stt, dx_sim, y_sim = oracle(RT.bf16_store)
+    blk = CitrinetBlock(cin, cout, repeat=rep, kernel_size=(K,), residual=res, separable=True)
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    blk = blk.cuda().train()
+    bt = BlockTrainer(blk)
+    l32 = torch.from_numpy(lens.astype(np.int32)).cuda()
+    yy, T_out, lo, tape = bt.forward(ops.pack_rows(torch.from_numpy(x).cuda(), l32), T, l32, zero_tail=True)
+    assert l2(ops.unpack_rows(yy, T_out).cpu().numpy(), np.where(m, y_sim, 0)) < 6e-3
+    dx = bt.backward(tape, ops.pack_rows(torch.from_numpy(Rm).cuda()), need_dx=True)
+    dxn = ops.unpack_rows(dx, T).cpu().numpy()
+    if rep <= 3:
+        # shallow: what is left against the bf16-storage oracle is backward rounding (measured 0.2-0.5 %)
+        assert l2(dxn, dx_sim) < 2e-2
+        for k, p in blk.named_parameters():
+            e = l2(p.grad.cpu().numpy(), stt[k].grad.numpy())
+            assert e < 2e-2, (k, e)
+    else:
+        # 5 sub-blocks: the single-ulp forward cascade (see the QuartzNet test above) also passes through the SE gate, and
+        # for the parameters fed by d loss / d mean_t(u) (last BN bias, fc.0) the bf16-storage oracle itself is 16-20 % away
+        # from the fp32 oracle while the device is within 7 % of fp32: accept closeness to EITHER reference
+        ref32, dx32, _ = oracle(None)
+        assert min(l2(dxn, dx_sim), l2(dxn, dx32)) < GRAD_TOL
+        for k, p in blk.named_parameters():
+            g = p.grad.cpu().numpy()
+            e = min(l2(g, stt[k].grad.numpy()), l2(g, ref32[k].grad.numpy()))
+            assert e < GRAD_TOL, (k, e)
+    for k, b in blk.named_buffers():
+        if "running" in k:
+            assert rel_err(b.cpu().numpy(), stt[k].detach().numpy())[0] < 1e-2, k

@@ -61,6 +61,12 @@ SIGNATURES = {
                               c_longlong, c_void_p]),
     "ts_resample": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_int, c_void_p]),
+    "ts_bn_apply_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                               c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ts_bn_bwd_reduce_se": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ts_bn_bwd_apply_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_prep_weights": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
     "ts_pw_gemm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p]),

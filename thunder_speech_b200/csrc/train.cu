@@ -70,7 +70,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
                                 const float* __restrict__ h, const __nv_bfloat16* __restrict__ zr,
                                 const float* __restrict__ sr, const float* __restrict__ hr, int C, int T, int pitch,
                                 const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ y,
-                                long long rows) {
+                                long long rows, const float* __restrict__ gate) {
   pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
   pdl_wait();
   const long long row = blockIdx.x;
@@ -81,8 +81,9 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
   float v[8], o[8];
   unpack8(*reinterpret_cast<const uint4*>(z + row * pitch + t), v);
   const float sc = s[c], sh = h[c];
+  const float gt = gate ? gate[row] : 1.f;   // SqueezeExcite: the main branch is scaled per (utterance, channel)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sc, sh);
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sc, sh) * gt;
   if (zr != nullptr) {
     unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), v);
     const float sc2 = sr[c], sh2 = hr[c];
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(RW * 32)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                      const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ zr, int T, int pitch,
                      long long rows, int relu, float* __restrict__ sums, int C, const float* __restrict__ ms,
-                     const float* __restrict__ mh, const float* __restrict__ msr, const float* __restrict__ mhr) {
+                     const float* __restrict__ mh, const float* __restrict__ msr, const float* __restrict__ mhr,
+                     const float* __restrict__ gate) {
   pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
   pdl_wait();
   const long long row = (long long)blockIdx.x * RW + (threadIdx.x >> 5);
@@ -114,6 +116,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   const int c = (int)(row % C);
   const float sc = remask ? ms[c] : 0.f, sh = remask ? mh[c] : 0.f;
   const float sc2 = (remask && zr != nullptr) ? msr[c] : 0.f, sh2 = (remask && zr != nullptr) ? mhr[c] : 0.f;
+  const float gt = gate ? gate[row] : 1.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   for (int t = lane * 8; t < T; t += 256) {
     float g[8], yy[8], zz[8], z2[8];
@@ -124,7 +127,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     if (remask) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float o = fmaf(zz[j], sc, sh);
+        float o = fmaf(zz[j], sc, sh) * gt;
         if (zr != nullptr) o += fmaf(z2[j], sc2, sh2);
         yy[j] = o;
       }
@@ -156,7 +159,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
                                     int pitch, int relu, __nv_bfloat16* __restrict__ dz,
                                     __nv_bfloat16* __restrict__ dzr, long long rows, const float* __restrict__ ms,
                                     const float* __restrict__ mh, const float* __restrict__ msr,
-                                    const float* __restrict__ mhr) {
+                                    const float* __restrict__ mhr, const float* __restrict__ gate,
+                                    const float* __restrict__ addc) {
   pdl_launch_dependents();   // PDL: the next kernel may start its prologue; then wait for the previous grid
   pdl_wait();
   const long long row = blockIdx.x;
@@ -171,8 +175,9 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
       unpack8(*reinterpret_cast<const uint4*>(y + row * pitch + t), yy);
     } else {   // recompute the forward pre-activation exactly as bn_apply_kernel did
       const float sc = ms[c], sh = mh[c];
+      const float gm = gate ? gate[row] : 1.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) yy[j] = fmaf(zz[j], sc, sh);
+      for (int j = 0; j < 8; ++j) yy[j] = fmaf(zz[j], sc, sh) * gm;
       if (zr != nullptr) {
         float z2[8];
         unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), z2);
@@ -186,8 +191,11 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
       if (!(yy[j] > 0.f)) g[j] = 0.f;
   }
   const float a = coef[3 * c], b = coef[3 * c + 1], cc = coef[3 * c + 2];
+  // SqueezeExcite: the gradient reaching the main branch's BatchNorm output is dym * gate[b,c] + addc[b,c] (the second
+  // term is d loss / d mean_t(u), spread over every frame); the residual branch below sees dym unchanged
+  const float gt = gate ? gate[row] : 1.f, ac = addc ? addc[row] : 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(a, g[j], fmaf(b, zz[j], cc)) : 0.f;
+  for (int j = 0; j < 8; ++j) o[j] = (t + j < T) ? fmaf(a, fmaf(g[j], gt, ac), fmaf(b, zz[j], cc)) : 0.f;
   *reinterpret_cast<uint4*>(dz + row * pitch + t) = pack8(o);
   if (zr != nullptr) {
     unpack8(*reinterpret_cast<const uint4*>(zr + row * pitch + t), zz);
@@ -270,7 +278,7 @@ extern "C" int ts_bn_apply(const void* z, const float* scale, const float* shift
   TS_CUDA(launch_pdl(train::bn_apply_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
                      (const __nv_bfloat16*)z, scale, shift,
                                                                  (const __nv_bfloat16*)zr, scale_r, shift_r, C, T, pitch,
-                                                                 lens, relu, (__nv_bfloat16*)y, rows));
+                                                                 lens, relu, (__nv_bfloat16*)y, rows, (const float*)nullptr));
   TS_LAUNCH_CHECK("bn_apply_kernel");
   return TS_OK;
 }
@@ -286,7 +294,7 @@ extern "C" int ts_bn_bwd_reduce(const void* dy, const void* y, const void* z, co
   TS_CUDA(launch_pdl(train::bn_bwd_reduce_kernel, dim3((unsigned)ceil_div64(rows, train::RW)), dim3(train::RW * 32), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
                      
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, T, pitch, rows,
-      relu, sums, C, mask_scale, mask_shift, mask_scale_r, mask_shift_r));
+      relu, sums, C, mask_scale, mask_shift, mask_scale_r, mask_shift_r, (const float*)nullptr));
   TS_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return TS_OK;
 }
@@ -307,7 +315,8 @@ extern "C" int ts_bn_bwd_apply(const void* dy, const void* y, const void* z, con
   TS_CUDA(launch_pdl(train::bn_bwd_apply_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
                      
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, coef, coef_r, C,
-      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows, mask_scale, mask_shift, mask_scale_r, mask_shift_r));
+      T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows, mask_scale, mask_shift, mask_scale_r, mask_shift_r,
+      (const float*)nullptr, (const float*)nullptr));
   TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TS_OK;
 }
@@ -741,5 +750,59 @@ extern "C" int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void*
                                                                     (const __nv_bfloat16*)x, T_in, pitch_in, len_in, B, C,
                                                                     K, S, D, P, bchunk, part);
   TS_LAUNCH_CHECK("dw_wgrad_kernel");
+  return TS_OK;
+}
+
+// ---- SqueezeExcite variants (Citrinet training): the main branch of the block's last sub-block is scaled by gate[b, c] ----
+extern "C" int ts_bn_apply_se(const void* z, const float* scale, const float* shift, const void* zr, const float* scale_r,
+                              const float* shift_r, const float* gate, int B, int C, int T, int pitch, const int32_t* lens,
+                              int relu, void* y, void* stream) {
+  TS_REQUIRE(z && scale && shift && gate && y, TS_ERR_INVALID, "ts_bn_apply_se: null pointer");
+  TS_REQUIRE((zr == nullptr) == (scale_r == nullptr) && (zr == nullptr) == (shift_r == nullptr), TS_ERR_INVALID,
+             "ts_bn_apply_se: residual operands disagree");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_apply_se: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_apply_se: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
+  TS_CUDA(launch_pdl(train::bn_apply_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     (const __nv_bfloat16*)z, scale, shift, (const __nv_bfloat16*)zr, scale_r, shift_r, C, T, pitch, lens, relu,
+                     (__nv_bfloat16*)y, rows, gate));
+  TS_LAUNCH_CHECK("bn_apply_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_reduce_se(const void* dy, const void* z, const void* zr, int B, int C, int T, int pitch, int relu,
+                                   float* sums, const float* mask_scale, const float* mask_shift,
+                                   const float* mask_scale_r, const float* mask_shift_r, const float* gate, void* stream) {
+  TS_REQUIRE(dy && z && sums && mask_scale && mask_shift && gate, TS_ERR_INVALID, "ts_bn_bwd_reduce_se: null pointer");
+  TS_REQUIRE(!zr || (mask_scale_r && mask_shift_r), TS_ERR_INVALID, "ts_bn_bwd_reduce_se: residual operands");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_reduce_se: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_CUDA(launch_pdl(train::bn_bwd_reduce_kernel, dim3((unsigned)ceil_div64(rows, train::RW)), dim3(train::RW * 32), 0,
+                     (cudaStream_t)stream, (option_pdl() & 2) != 0, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)nullptr,
+                     (const __nv_bfloat16*)z, (const __nv_bfloat16*)zr, T, pitch, rows, relu, sums, C, mask_scale, mask_shift,
+                     mask_scale_r, mask_shift_r, gate));
+  TS_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_bn_bwd_apply_se(const void* dy, const void* z, const void* zr, const float* coef, const float* coef_r, int B,
+                                  int C, int T, int pitch, int relu, void* dz, void* dzr, const float* mask_scale,
+                                  const float* mask_shift, const float* mask_scale_r, const float* mask_shift_r,
+                                  const float* gate, const float* addc, void* stream) {
+  TS_REQUIRE(dy && z && coef && dz && mask_scale && mask_shift && gate && addc, TS_ERR_INVALID,
+             "ts_bn_bwd_apply_se: null pointer");
+  TS_REQUIRE((zr == nullptr) == (coef_r == nullptr) && (zr == nullptr) == (dzr == nullptr), TS_ERR_INVALID,
+             "ts_bn_bwd_apply_se: residual operands disagree");
+  TS_REQUIRE(!zr || (mask_scale_r && mask_shift_r), TS_ERR_INVALID, "ts_bn_bwd_apply_se: residual mask operands");
+  TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T && pitch % 8 == 0, TS_ERR_INVALID, "ts_bn_bwd_apply_se: bad sizes");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_bn_bwd_apply_se: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
+  TS_CUDA(launch_pdl(train::bn_bwd_apply_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     (const __nv_bfloat16*)dy, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)z,
+                     (const __nv_bfloat16*)zr, coef, coef_r, C, T, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dzr, rows,
+                     mask_scale, mask_shift, mask_scale_r, mask_shift_r, gate, addc));
+  TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TS_OK;
 }

@@ -164,6 +164,39 @@ def bn_bwd_apply_fused(dy: Tensor, z: Tensor, bn: nn.BatchNorm1d, stats: Tensor,
     return dz, dzr
 
 
+def bn_apply_se(z, scale, shift, zr, scale_r, shift_r, gate, T, lens, relu=True) -> Tensor:
+    """y = act(gate[b,c] * BN(z) [+ BN_r(zr)]): the last sub-block of a Citrinet block (SqueezeExcite scale)."""
+    B, C, pitch = z.shape
+    y = torch.empty_like(z)
+    with ops._timed("bn_apply", bytes=B * C * T * 2 * (3 if zr is not None else 2), flops=0):
+        _lib.check(_lib.lib().ts_bn_apply_se(_p(z), _p(scale), _p(shift), _p(zr), _p(scale_r), _p(shift_r), _p(gate), B, C, T,
+                                             pitch, _p(lens), int(relu), _p(y), _stream()), "ts_bn_apply_se")
+    return y
+
+
+def bn_bwd_reduce_se(dy, z, zr, T, mask, gate, relu=True) -> Tensor:
+    """Per-utterance partial sums [B, C, 3] = (sum dym, sum dym*z, sum dym*zr), the ReLU mask rebuilt with the SE gate."""
+    B, C, pitch = z.shape
+    sums = torch.empty((B, C, 3), device=z.device, dtype=torch.float32)
+    with ops._timed("bn_bwd_reduce", bytes=B * C * T * 2 * (3 if zr is not None else 2), flops=0):
+        _lib.check(_lib.lib().ts_bn_bwd_reduce_se(_p(dy), _p(z), _p(zr), B, C, T, pitch, int(relu), _p(sums), _p(mask[0]),
+                                                  _p(mask[1]), _p(mask[2]), _p(mask[3]), _p(gate), _stream()),
+                   "ts_bn_bwd_reduce_se")
+    return sums
+
+
+def bn_bwd_apply_se(dy, z, zr, coef, coef_r, T, mask, gate, addc, relu=True) -> Tuple[Tensor, Optional[Tensor]]:
+    """dz = a (dym gate + addc) + b z + c0;  dzr = a_r dym + b_r zr + c0_r."""
+    B, C, pitch = z.shape
+    dz = torch.empty_like(z)
+    dzr = torch.empty_like(z) if zr is not None else None
+    with ops._timed("bn_bwd_apply", bytes=B * C * T * 2 * (6 if zr is not None else 4), flops=0):
+        _lib.check(_lib.lib().ts_bn_bwd_apply_se(_p(dy), _p(z), _p(zr), _p(coef), _p(coef_r), B, C, T, pitch, int(relu),
+                                                 _p(dz), _p(dzr), _p(mask[0]), _p(mask[1]), _p(mask[2]), _p(mask[3]),
+                                                 _p(gate), _p(addc), _stream()), "ts_bn_bwd_apply_se")
+    return dz, dzr
+
+
 def bn_apply(z, scale, shift, zr, scale_r, shift_r, T, lens, relu=True) -> Tensor:
     B, C, pitch = z.shape
     y = torch.empty_like(z)
@@ -366,6 +399,7 @@ class BlockTrainer:
 
         self.block = block
         self.subs: List[_Sub] = []
+        self.se: Optional[nn.Module] = None
         pending = []
         for layer in block.mconv.children():
             if isinstance(layer, MaskedConv1d):
@@ -383,7 +417,7 @@ class BlockTrainer:
                     self.subs.append(_Sub(None, pwl.conv, inner, 1, 1, 1, 0))
                 pending = []
             elif hasattr(inner, "fc"):
-                raise NotImplementedError("training step: SqueezeExcite (Citrinet) backward is not implemented yet")
+                self.se = inner          # SqueezeExcite after the last BatchNorm (citrinet/blocks.py:154)
         self.res = None
         if block.res is not None:
             rl = list(block.res.children())
@@ -427,7 +461,27 @@ class BlockTrainer:
             z, zst = pw_gemm_stats(wpw, a, Ta)
             nn_ = B * Ta
             rec = dict(x=cur, Tin=Tc, lin=lc, a=a, Ta=Ta, la=la, z=z, n=nn_)
-            if last and self.res is not None:
+            if last and self.se is not None:
+                # SqueezeExcite: u = BN(z); gate = sigmoid(W2 relu(W1 mean_t u)); y = relu(gate * u [+ BN_r(zr)]).
+                # mean_t u over ALL Ta frames (the reference pools the unmasked BatchNorm output, citrinet/blocks.py:70-83)
+                # follows from the row sums the GEMM epilogue already produced: sum_t u = scale * sum_t z + Ta * shift.
+                scale, shift, mean, inv = bn_finalize(zst, nn_, sb.bn, update_running)
+                rowsum = zst[..., 0].sum(2) if zst.dim() == 4 else zst[..., 0]
+                pool = torch.addcmul(shift * float(Ta), rowsum, scale).contiguous()            # [B, C] sum_t u
+                w1 = self.se.fc[0].weight.detach().float().contiguous()
+                w2 = self.se.fc[2].weight.detach().float().contiguous()
+                gate = ops.se_fc(pool, Ta, w1, w2)
+                zr = st_r = None
+                sc_r = sh_r = None
+                if self.res is not None:
+                    rconv, rbn = self.res
+                    zr, zrst = pw_gemm_stats(self.pack.get(rconv.weight)[0], x, T)
+                    sc_r, sh_r, mean_r, inv_r = bn_finalize(zrst, B * T, rbn, update_running)
+                    st_r = torch.stack([sc_r, sh_r, mean_r, inv_r])
+                y = bn_apply_se(z, scale, shift, zr, sc_r, sh_r, gate, Ta, la if zero_tail else None, True)
+                rec.update(zr=zr, stats=torch.stack([scale, shift, mean, inv]), stats_r=st_r, gate=gate, pool=pool,
+                           rowsum=rowsum)
+            elif last and self.res is not None:
                 rconv, rbn = self.res
                 wr = self.pack.get(rconv.weight)[0]
                 zr, zrst = pw_gemm_stats(wr, x, T)
@@ -449,6 +503,33 @@ class BlockTrainer:
                 torch._foreach_add_(nbt, 1)
         return y, Tc, lc, tape
 
+    def _se_backward(self, g: Tensor, rec, sb: _Sub, zr: Optional[Tensor], mask, Ta: int, has_res: bool):
+        """BatchNorm + SqueezeExcite + (residual) + ReLU backward of a Citrinet block's last sub-block.
+
+        With u = BN(z) and dym = dy * relu':  d gate[b,c] = sum_t dym u = scale sum_t(dym z) + shift sum_t(dym)  (from the
+        per-utterance partial sums, no extra pass);  the two FCs are [B, C] / [B, C/8] matrices -- torch.matmul;
+        d u = dym gate + dm / Ta with dm = d loss / d mean_t(u), so the BatchNorm-backward sums become
+        sum du = sum_b (gate s0 + dm),  sum du z = sum_b (gate s1 + dm/Ta rowsum_z)."""
+        st, st_r = rec["stats"], rec.get("stats_r")
+        gate, pool, rowsum = rec["gate"], rec["pool"], rec["rowsum"]
+        sums = bn_bwd_reduce_se(g, rec["z"], zr, Ta, mask, gate)               # [B, C, 3]
+        s0, s1 = sums[..., 0], sums[..., 1]
+        dgate = st[0] * s1 + st[1] * s0
+        w1, w2 = self.se.fc[0].weight.detach().float(), self.se.fc[2].weight.detach().float()
+        m = pool / float(Ta)
+        hpre = m @ w1.t()
+        h = torch.relu(hpre)
+        ds = dgate * gate * (1.0 - gate)
+        _grad(self.se.fc[2].weight).copy_(ds.t() @ h)
+        dh = (ds @ w2) * (hpre > 0)
+        _grad(self.se.fc[0].weight).copy_(dh.t() @ m)
+        dm = dh @ w1
+        addc = (dm / float(Ta)).contiguous()
+        part = torch.stack([gate * s0 + dm, gate * s1 + addc * rowsum, torch.zeros_like(s0)], dim=-1).contiguous()
+        coef = bn_bwd_coef(part, 1, rec["n"], sb.bn, st[2], st[3])
+        coef_r = bn_bwd_coef(sums, 2, rec["n"], self.res[1], st_r[2], st_r[3]) if has_res else None
+        return bn_bwd_apply_se(g, rec["z"], zr, coef, coef_r, Ta, mask, gate, addc)
+
     # -- backward --------------------------------------------------------------------------------------
     def backward(self, tape, dy: Tensor, need_dx: bool = True, side: Optional[_SideStream] = None) -> Optional[Tensor]:
         """``side``: the caller's side stream (the caller joins it); None = own side stream, joined before returning."""
@@ -466,10 +547,13 @@ class BlockTrainer:
             # the ReLU mask is rebuilt from z with the forward scale / shift (y is not read again)
             st, st_r = rec["stats"], rec.get("stats_r")
             zr = rec.get("zr") if has_res else None
-            sums = bn_bwd_reduce(g, None, rec["z"], zr, Ta, True, partial=True,
-                                 mask=(st[0], st[1], st_r[0] if has_res else None, st_r[1] if has_res else None))
-            dz, dzr = bn_bwd_apply_fused(g, rec["z"], sb.bn, st, zr, self.res[1] if has_res else None,
-                                         st_r if has_res else None, sums, Ta, True)
+            mask = (st[0], st[1], st_r[0] if has_res else None, st_r[1] if has_res else None)
+            if last and self.se is not None:
+                dz, dzr = self._se_backward(g, rec, sb, zr, mask, Ta, has_res)
+            else:
+                sums = bn_bwd_reduce(g, None, rec["z"], zr, Ta, True, partial=True, mask=mask)
+                dz, dzr = bn_bwd_apply_fused(g, rec["z"], sb.bn, st, zr, self.res[1] if has_res else None,
+                                             st_r if has_res else None, sums, Ta, True)
             # pointwise conv: weight gradient on the tensor cores, input gradient = W^T dz (masked like `a` was)
             side.run(lambda dz=dz, rec=rec, sb=sb, Ta=Ta: pw_wgrad(dz, rec["a"], Ta, out=_grad(sb.pw.weight)), dz)
             first = r == 0
