@@ -204,6 +204,10 @@ int ts_pw_wgrad_reduce(const float* part, int nsplit, long long n, float* out, v
 int ts_dw_wgrad(const void* da, int T_out, int pitch_out, const void* x, int T_in, int pitch_in, const int32_t* len_in,
                 int B, int C, int K, int S, int D, int P, int bchunk, int flags, float* part, void* stream);
 
+/* Transpose of ts_gather_rows (backward of strided layers): dst[b,c,t] = src[b,c,t/S] where S divides t and t/S < T_src, else
+ * 0, for t < T_dst (zero up to pitch_dst); `accumulate` adds onto the existing dst instead.  bf16 rows. */
+int ts_scatter_rows(const void* src, int B, int C, int T_src, int pitch_src, int S, void* dst, int T_dst, int pitch_dst,
+                    int accumulate, void* stream);
 /* SqueezeExcite variants for Citrinet training (citrinet/blocks.py:48-83,177-197): the main branch of a block's last
  * sub-block is u = BN(z) scaled by gate[b, c] = sigmoid(W2 relu(W1 mean_t u)) before the residual add and ReLU.
  *   ts_bn_apply_se:      y = act(gate[b,c] * (z*scale+shift) (+ zr*scale_r+shift_r)), tail zeroed

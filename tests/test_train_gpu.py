@@ -496,3 +496,68 @@ def test_citrinet_block_with_squeeze_excite_training(cin, cout, K, rep, B, T, re
     for k, b in blk.named_buffers():
         if "running" in k:
             assert rel_err(b.cpu().numpy(), stt[k].detach().numpy())[0] < 1e-2, k
+
+
+@pytest.mark.parametrize("cin,cout,K,rep,B,T,res", [(64, 128, 11, 3, 4, 201, True), (32, 64, 5, 1, 6, 100, True),
+                                                     (256, 256, 13, 2, 4, 333, False)])
+def test_strided_citrinet_block_training(cin, cout, K, rep, B, T, res):
+    """Stride-2 CitrinetBlock (last sub-block strided, strided 1x1 residual, SqueezeExcite): forward, dx and every gradient
+    against the autograd torch port with bf16 storage simulated.  Covers the transposed depthwise conv (zero-upsample +
+    flipped taps), the strided weight gradient and ts_scatter_rows."""
+    from oracle import ref_torch as RT
+    from thunder_speech_b200.citrinet.blocks import CitrinetBlock
+
+    rng = np.random.Generator(np.random.PCG64(7 * cin + K + rep))
+    st = synth.block_state(rng, "", cin, cout, rep, K, res, True, se=True)
+    x = np.maximum(rng.standard_normal((B, cin, T)), 0).astype(np.float32)
+    lens = np.sort(rng.integers(T // 2, T + 1, B))[::-1].astype(np.int64).copy()
+    lens[0] = T
+    To = (T - 1) // 2 + 1
+    lo_ref = (lens - 1) // 2 + 1
+    m = (np.arange(T)[None, :] < lens[:, None])[:, None, :]
+    mo = (np.arange(To)[None, :] < lo_ref[:, None])[:, None, :]
+    Rm = np.where(mo, rng.standard_normal((B, cout, To)), 0).astype(np.float32)
+    cfg = R.BlockCfg(cin, cout, repeat=rep, kernel_size=K, stride=2, residual=res, separable=True, kind="citrinet")
+    stt = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st.items()}
+    for k, v in stt.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    xt = torch.from_numpy(np.where(m, x, 0).astype(np.float32)).requires_grad_(True)
+    y, yl = RT.block(xt, torch.from_numpy(lens), cfg, stt, "", train=True, store=RT.bf16_store)
+    assert y.shape[-1] == To and np.array_equal(yl.numpy(), lo_ref)
+    (y * torch.from_numpy(Rm)).sum().backward()
+    blk = CitrinetBlock(cin, cout, repeat=rep, kernel_size=(K,), stride=(2,), residual=res, separable=True)
+    blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    blk = blk.cuda().train()
+    bt = BlockTrainer(blk)
+    l32 = torch.from_numpy(lens.astype(np.int32)).cuda()
+    yy, T_out, lo, tape = bt.forward(ops.pack_rows(torch.from_numpy(x).cuda(), l32), T, l32, zero_tail=True)
+    assert T_out == To and np.array_equal(lo.cpu().numpy(), lo_ref)
+    assert l2(ops.unpack_rows(yy, T_out).cpu().numpy(), np.where(mo, y.detach().numpy(), 0)) < 6e-3
+    dx = bt.backward(tape, ops.pack_rows(torch.from_numpy(Rm).cuda()), need_dx=True)
+    dxn = ops.unpack_rows(dx, T).cpu().numpy()
+    assert np.all(np.where(m, 0, dxn) == 0)                      # nothing flows into frames beyond the utterance
+    assert l2(dxn, xt.grad.numpy()) < 2e-2
+    for k, p in blk.named_parameters():
+        e = l2(p.grad.cpu().numpy(), stt[k].grad.numpy())
+        assert e < 2e-2, (k, e)
+
+
+def test_scatter_rows_is_the_transpose_of_gather_rows():
+    from thunder_speech_b200.train import scatter_rows
+
+    rng = np.random.default_rng(9)
+    B, C, T, S = 3, 5, 201, 2
+    Ts = (T - 1) // S + 1
+    src = ops.pack_rows(torch.from_numpy(rng.standard_normal((B, C, Ts)).astype(np.float32)).cuda())
+    up = scatter_rows(src, Ts, S, T)
+    u = ops.unpack_rows(up, T).cpu().numpy()
+    sv = ops.unpack_rows(src, Ts).cpu().numpy()
+    assert np.array_equal(u[:, :, ::S], sv) and np.all(u[:, :, 1::S] == 0) and np.all(up[:, :, T:].float().cpu().numpy() == 0)
+    base = ops.pack_rows(torch.from_numpy(rng.standard_normal((B, C, T)).astype(np.float32)).cuda())
+    b0 = ops.unpack_rows(base, T).cpu().numpy()
+    acc = ops.unpack_rows(scatter_rows(src, Ts, S, T, dst=base), T).cpu().numpy()
+    exp = b0.copy()
+    exp[:, :, ::S] += sv
+    assert np.abs(acc - exp).max() <= 2 ** -8 * np.abs(exp).max()
+    assert np.array_equal(ops.unpack_rows(ops.gather_rows(up, T, S, None), Ts).cpu().numpy(), sv)

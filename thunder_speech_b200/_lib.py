@@ -61,6 +61,7 @@ SIGNATURES = {
                               c_longlong, c_void_p]),
     "ts_resample": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_int, c_void_p]),
+    "ts_scatter_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ts_bn_apply_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ts_bn_bwd_reduce_se": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

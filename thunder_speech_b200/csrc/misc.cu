@@ -384,3 +384,61 @@ extern "C" int ts_spec_mask(void* feat, int dtype, int B, int C, int T, int pitc
   TS_LAUNCH_CHECK("spec_mask_kernel");
   return TS_OK;
 }
+
+// ---- scatter_rows: the transpose of gather_rows (training backward of strided layers) --------------------------------
+// dst[b, c, t] = (t % S == 0 && t / S < T_src) ? src[b, c, t / S] : 0   for t < T_dst (zero up to the pitch), plus the old
+// dst value when `accumulate`.  Zero-upsampling turns a strided depthwise conv's input gradient into a stride-1 conv with
+// flipped taps; with accumulate it adds a strided 1x1 residual conv's input gradient onto the main-branch gradient.
+namespace ts {
+namespace misc {
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, int T_src, int pitch_src, int S,
+                                    __nv_bfloat16* __restrict__ dst, int T_dst, int pitch_dst, int accumulate,
+                                    long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x;
+  const int t0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t0 >= pitch_dst) return;
+  const __nv_bfloat16* sr = src + row * pitch_src;
+  __nv_bfloat16* dr = dst + row * pitch_dst + t0;
+  uint4 old = make_uint4(0, 0, 0, 0);
+  if (accumulate) old = *reinterpret_cast<const uint4*>(dr);
+  const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int t = t0 + 2 * h + e;
+      float val = 0.f;
+      if (t < T_dst) {
+        if (accumulate) val = __uint_as_float(e == 0 ? (ow[h] << 16) : (ow[h] & 0xFFFF0000u));
+        const int q = t / S;
+        if (q * S == t && q < T_src) val += __bfloat162float(sr[q]);
+      }
+      v[e] = val;
+    }
+    __nv_bfloat162 pr = __floats2bfloat162_rn(v[0], v[1]);
+    o[h] = *reinterpret_cast<uint32_t*>(&pr);
+  }
+  *reinterpret_cast<uint4*>(dr) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+}  // namespace misc
+}  // namespace ts
+
+extern "C" int ts_scatter_rows(const void* src, int B, int C, int T_src, int pitch_src, int S, void* dst, int T_dst,
+                               int pitch_dst, int accumulate, void* stream) {
+  TS_REQUIRE(src && dst, TS_ERR_INVALID, "ts_scatter_rows: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T_src > 0 && T_dst > 0 && S > 0 && pitch_src >= T_src && pitch_dst >= T_dst &&
+                 pitch_dst % 8 == 0,
+             TS_ERR_INVALID, "ts_scatter_rows: bad sizes");
+  TS_REQUIRE((T_src - 1) * S < T_dst, TS_ERR_INVALID, "ts_scatter_rows: source does not fit: (T_src-1)*S >= T_dst");
+  const long long rows = (long long)B * C;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_scatter_rows: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch_dst / 8, 128));
+  TS_CUDA(launch_pdl(misc::scatter_rows_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (option_pdl() & 2) != 0,
+                     (const __nv_bfloat16*)src, T_src, pitch_src, S, (__nv_bfloat16*)dst, T_dst, pitch_dst, accumulate, rows));
+  TS_LAUNCH_CHECK("scatter_rows_kernel");
+  return TS_OK;
+}

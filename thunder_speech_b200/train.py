@@ -164,6 +164,18 @@ def bn_bwd_apply_fused(dy: Tensor, z: Tensor, bn: nn.BatchNorm1d, stats: Tensor,
     return dz, dzr
 
 
+def scatter_rows(src: Tensor, T_src: int, S: int, T_dst: int, dst: Optional[Tensor] = None) -> Tensor:
+    """Transpose of ``ops.gather_rows``: ``dst[:, :, t*S] (+)= src[:, :, t]``; a fresh zero-filled tensor unless ``dst`` is
+    given (then accumulated in place)."""
+    B, C, ps = src.shape
+    acc = dst is not None
+    if dst is None:
+        dst = torch.empty((B, C, ops.row_pitch(T_dst)), device=src.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ts_scatter_rows(_p(src), B, C, T_src, ps, S, _p(dst), T_dst, dst.shape[2], int(acc), _stream()),
+               "ts_scatter_rows")
+    return dst
+
+
 def bn_apply_se(z, scale, shift, zr, scale_r, shift_r, gate, T, lens, relu=True) -> Tensor:
     """y = act(gate[b,c] * BN(z) [+ BN_r(zr)]): the last sub-block of a Citrinet block (SqueezeExcite scale)."""
     B, C, pitch = z.shape
@@ -400,6 +412,7 @@ class BlockTrainer:
         self.block = block
         self.subs: List[_Sub] = []
         self.se: Optional[nn.Module] = None
+        self.res_stride = 1
         pending = []
         for layer in block.mconv.children():
             if isinstance(layer, MaskedConv1d):
@@ -421,9 +434,8 @@ class BlockTrainer:
         self.res = None
         if block.res is not None:
             rl = list(block.res.children())
-            if rl[0].stride != 1:
-                raise NotImplementedError("training step: strided residual branches are not implemented yet")
             self.res = (rl[0].conv, rl[1].layer[0])
+            self.res_stride = int(rl[0].stride)
         self.pack: Optional[WeightPack] = None      # set by EncoderTrainer (one pack for the whole model)
         self._own_pack = False
 
@@ -444,6 +456,12 @@ class BlockTrainer:
         if self._own_pack:
             self.pack.refresh()
         tape = dict(x=x, T=T, lens=lens, subs=[])
+        # input of the residual 1x1 conv: every res_stride-th frame (citrinet/blocks.py:140-159)
+        xr_in, Tr = x, T
+        if self.res is not None and self.res_stride != 1:
+            xr_in = ops.gather_rows(x, T, self.res_stride, lens)
+            Tr = (T - 1) // self.res_stride + 1
+        tape.update(xr=xr_in, Tr=Tr)
         cur, Tc, lc = x, T, lens
         B = x.shape[0]
         n = len(self.subs)
@@ -475,8 +493,10 @@ class BlockTrainer:
                 sc_r = sh_r = None
                 if self.res is not None:
                     rconv, rbn = self.res
-                    zr, zrst = pw_gemm_stats(self.pack.get(rconv.weight)[0], x, T)
-                    sc_r, sh_r, mean_r, inv_r = bn_finalize(zrst, B * T, rbn, update_running)
+                    if Tr != Ta:
+                        raise ValueError(f"residual branch length {Tr} != main branch length {Ta}")
+                    zr, zrst = pw_gemm_stats(self.pack.get(rconv.weight)[0], xr_in, Tr)
+                    sc_r, sh_r, mean_r, inv_r = bn_finalize(zrst, B * Tr, rbn, update_running)
                     st_r = torch.stack([sc_r, sh_r, mean_r, inv_r])
                 y = bn_apply_se(z, scale, shift, zr, sc_r, sh_r, gate, Ta, la if zero_tail else None, True)
                 rec.update(zr=zr, stats=torch.stack([scale, shift, mean, inv]), stats_r=st_r, gate=gate, pool=pool,
@@ -484,7 +504,9 @@ class BlockTrainer:
             elif last and self.res is not None:
                 rconv, rbn = self.res
                 wr = self.pack.get(rconv.weight)[0]
-                zr, zrst = pw_gemm_stats(wr, x, T)
+                if Tr != Ta:
+                    raise ValueError(f"residual branch length {Tr} != main branch length {Ta}")
+                zr, zrst = pw_gemm_stats(wr, xr_in, Tr)
                 y, st, st_r = bn_apply_fused(z, zst, sb.bn, zr, zrst, rbn, Ta, la if zero_tail else None, True,
                                              update_running)
                 rec.update(zr=zr, stats=st, stats_r=st_r)
@@ -567,25 +589,35 @@ class BlockTrainer:
                     da, Ta, rec["x"], rec["Tin"], rec["lin"], sb.K, sb.S, sb.D, sb.P, out=_grad(sb.dw.weight),
                     premasked=True), da)
                 if (not first) or need_dx:
-                    if sb.S != 1:
-                        raise NotImplementedError("training step: input gradient of a strided depthwise conv")
                     wflip = self.pack.get(sb.dw.weight)[1]
-                    g = ops.dw_conv(da, Ta, wflip, 1, sb.D, sb.D * (sb.K - 1) - sb.P, rec["lin"], True)
+                    if sb.S != 1:
+                        # transposed conv = stride-1 conv of the zero-upsampled gradient with flipped taps
+                        da_up = scatter_rows(da, Ta, sb.S, rec["Tin"])
+                        side.keep.append(da_up)
+                        g = ops.dw_conv(da_up, rec["Tin"], wflip, 1, sb.D, sb.D * (sb.K - 1) - sb.P, rec["lin"], True)
+                    else:
+                        g = ops.dw_conv(da, Ta, wflip, 1, sb.D, sb.D * (sb.K - 1) - sb.P, rec["lin"], True)
                 else:
                     g = None
             else:
                 g = da
             if has_res:
                 rconv, rbn = self.res
-                side.run(lambda dzr=dzr, rconv=rconv: pw_wgrad(dzr, tape["x"], tape["T"], out=_grad(rconv.weight)), dzr)
+                side.run(lambda dzr=dzr, rconv=rconv: pw_wgrad(dzr, tape["xr"], tape["Tr"], out=_grad(rconv.weight)), dzr)
                 if need_dx:
                     dx_res = dzr
         if need_dx and self.res is not None:
             # dx = dx_main + W_r^T dz_r, masked by the block-input lengths (epilogue: acc + 1 * y1)
             rconv, _ = self.res
             wrT = self.pack.get(rconv.weight)[1]
-            ones = torch.ones((g.shape[0], wrT.shape[0]), device=g.device, dtype=torch.float32)
-            g = ops.pw_gemm(wrT, dx_res, None, None, tape["T"], None, tape["lens"], False, False, None, ones, g)
+            if self.res_stride == 1:
+                ones = torch.ones((g.shape[0], wrT.shape[0]), device=g.device, dtype=torch.float32)
+                g = ops.pw_gemm(wrT, dx_res, None, None, tape["T"], None, tape["lens"], False, False, None, ones, g)
+            else:   # strided residual: its input gradient lands on every res_stride-th frame of dx
+                # frame q of the strided branch reads x[q * stride]: valid iff q < ceil(len / stride) = the output length
+                dxr = ops.pw_gemm(wrT, dx_res, None, None, tape["Tr"], None, tape["subs"][-1]["la"], False, False, None, None,
+                                  None)
+                g = scatter_rows(dxr, tape["Tr"], self.res_stride, tape["T"], dst=g)
         if own_side:
             side.join()
         return g if need_dx else None
