@@ -267,7 +267,8 @@ def test_block_gradients_vs_bf16_storage_oracle(cin, cout, K, rep, B, T, res):
         assert e < tol, (k, e)
 
 
-@pytest.mark.parametrize("B,V,T,Lmax,seed", [(6, 29, 101, 12, 0), (3, 29, 376, 120, 1), (4, 5, 40, 30, 2), (2, 200, 33, 7, 3)])
+@pytest.mark.parametrize("B,V,T,Lmax,seed", [(6, 29, 101, 12, 0), (3, 29, 376, 120, 1), (4, 5, 40, 30, 2), (2, 200, 33, 7, 3),
+                                              (3, 1025, 70, 20, 4)])
 def test_ctc_loss_kernel_vs_torch(B, V, T, Lmax, seed):
     """ts_ctc_loss against log_softmax + F.ctc_loss(reduction="mean", zero_infinity=True) (src/thunder/ctc_loss.py:15-47)
     in float64 on the CPU: per-utterance loss and the gradient w.r.t. the logits.  Covers ragged input / target lengths,

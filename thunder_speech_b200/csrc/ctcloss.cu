@@ -9,7 +9,7 @@
 // double-buffered shared memory, the next frame's log-probability prefetched from global memory).  alpha / beta go to a
 // scratch [B, T, Sp] for the gradient kernel; nll[b] = -logaddexp(alpha_{len-1}(S-1), alpha_{len-1}(S-2)).
 //
-// ctc_grad_kernel: a warp per frame, lane = class.  With y_t = softmax and the identity
+// ctc_grad_kernel: a CTA per (64 frames, utterance, 128 classes).  With y_t = softmax and the identity
 //   sum_s alpha_t(s) beta_t(s) / y_t(l'_s) = P(l | x)   (both recursions include y_t(l'_s)),
 //   d nll / d logit[c, t] = y_t(c) - sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - lp_t(c) + nll)
 // scaled by gscale / (B * max(target_len, 1)) ("mean" reduction) and zero for t >= len or a non-finite nll
@@ -140,8 +140,13 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, int V, int T, int pitch,
   }
 }
 
-constexpr int GT = 64;   // frames per CTA of the gradient kernel
+constexpr int GT = 64;    // frames per CTA of the gradient kernel
+constexpr int CH = 128;   // classes per CTA (grid.z walks the vocabulary in chunks: any V)
 
+// grid (ceil(pitch / GT), B, ceil(V / CH)).  Phase A: tile[c][t] = softmax_t(c) * scale for the chunk's classes.  Phase B:
+// one thread per frame walks the S states in order and subtracts the occupancy exp(alpha + beta - lp + nll) * scale from the
+// row of the state's label -- sequential per frame, so the sum over repeated labels has a fixed order (deterministic) and
+// the cost is O(S) per frame instead of O(V * S).
 __global__ void __launch_bounds__(256)
 ctc_grad_kernel(const float* __restrict__ logits, int V, int Vp, int T, int lpitch, int pitch,
                 const int32_t* __restrict__ in_len,
@@ -150,16 +155,17 @@ ctc_grad_kernel(const float* __restrict__ logits, int V, int Vp, int T, int lpit
                 const float* __restrict__ nll, float gscale, int B, float* __restrict__ loss_out,
                 __nv_bfloat16* __restrict__ grad) {
   extern __shared__ float sm[];
-  float* tile = sm;                                 // [V][GT + 1]
-  int* lab = reinterpret_cast<int*>(tile + V * (GT + 1));   // [Sp]
-  const int b = blockIdx.y, t0 = blockIdx.x * GT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* tile = sm;                                          // [CH][GT + 1]
+  int* lab = reinterpret_cast<int*>(tile + CH * (GT + 1));   // [Sp]
+  const int b = blockIdx.y, t0 = blockIdx.x * GT, c0 = blockIdx.z * CH, tid = threadIdx.x;
+  const int nc = min(CH, V - c0);
   const int len = min(max(in_len[b], 0), T);
   const int L = clamp_ll(tgt_len[b], 0, Lmax);
   const int S = 2 * L + 1;
   const float n = nll[b];
   const bool ok = isfinite(n) && len > 0;
   const float scale = ok ? gscale / ((float)B * (float)max(L, 1)) : 0.f;
-  if (blockIdx.x == 0 && tid == 0) loss_out[b] = ok ? n / (float)max(L, 1) : 0.f;
+  if (blockIdx.x == 0 && blockIdx.z == 0 && tid == 0) loss_out[b] = ok ? n / (float)max(L, 1) : 0.f;
   for (int s = tid; s < Sp; s += blockDim.x) {
     int l = blank;
     if ((s & 1) && s < S) {
@@ -167,32 +173,38 @@ ctc_grad_kernel(const float* __restrict__ logits, int V, int Vp, int T, int lpit
     }
     lab[s] = l;
   }
-  __syncthreads();
   const float* lg = logits + (size_t)b * V * lpitch;
-  for (int tt = warp; tt < GT; tt += 8) {
-    const int t = t0 + tt;
-    const bool live = ok && t < len;   // warp-uniform
-    for (int c = lane; c < V; c += 32) {
-      float g = 0.f;
-      if (live) {
-        const float lp = lg[(size_t)c * lpitch + t] - lse[(size_t)b * T + t];
-        const float* a = alpha + ((size_t)b * T + t) * Sp;
-        const float* be = beta + ((size_t)b * T + t) * Sp;
-        float occ = 0.f;
-        for (int s = 0; s < S; ++s) {
-          if (lab[s] == c) occ += expf(a[s] + be[s] - lp + n);
+  // phase A: softmax term (frames are the fast index: coalesced reads of the logit rows)
+  for (int i = tid; i < nc * GT; i += blockDim.x) {
+    const int c = i / GT, tt = i - c * GT, t = t0 + tt;
+    float g = 0.f;
+    if (ok && t < len) g = expf(lg[(size_t)(c0 + c) * lpitch + t] - lse[(size_t)b * T + t]) * scale;
+    tile[c * (GT + 1) + tt] = g;
+  }
+  __syncthreads();
+  // phase B: occupancy term, one thread per frame
+  if (tid < GT) {
+    const int t = t0 + tid;
+    if (ok && t < len) {
+      const float* a = alpha + ((size_t)b * T + t) * Sp;
+      const float* be = beta + ((size_t)b * T + t) * Sp;
+      const float ls = lse[(size_t)b * T + t];
+      for (int s = 0; s < S; ++s) {
+        const int c = lab[s] - c0;
+        if (c >= 0 && c < nc) {
+          const float lp = lg[(size_t)(c0 + c) * lpitch + t] - ls;
+          tile[c * (GT + 1) + tid] -= expf(a[s] + be[s] - lp + n) * scale;
         }
-        g = (expf(lp) - occ) * scale;
       }
-      tile[c * (GT + 1) + tt] = g;
     }
   }
   __syncthreads();
   // rows [V..Vp) stay as the caller zero-initialised them; frames >= T up to the pitch are zeroed here
   const int tmax = min(GT, pitch - t0);
-  for (int i = tid; i < V * GT; i += blockDim.x) {
+  for (int i = tid; i < nc * GT; i += blockDim.x) {
     const int c = i / GT, tt = i - c * GT;
-    if (tt < tmax) grad[((size_t)b * Vp + c) * pitch + t0 + tt] = __float2bfloat16((t0 + tt < T) ? tile[c * (GT + 1) + tt] : 0.f);
+    if (tt < tmax)
+      grad[((size_t)b * Vp + c0 + c) * pitch + t0 + tt] = __float2bfloat16((t0 + tt < T) ? tile[c * (GT + 1) + tt] : 0.f);
   }
 }
 
@@ -210,7 +222,6 @@ extern "C" int ts_ctc_loss(const float* logits, int B, int V, int T, int pitch, 
   TS_REQUIRE(blank >= 0 && blank < V, TS_ERR_INVALID, "ts_ctc_loss: blank index outside the vocabulary");
   const int S = 2 * Lmax + 1;
   TS_REQUIRE(S <= ctc::MAX_NS * ctc::ROLE_THREADS, TS_ERR_UNSUPPORTED, "ts_ctc_loss: target length > 511");
-  TS_REQUIRE(V <= 256, TS_ERR_UNSUPPORTED, "ts_ctc_loss: vocabulary > 256 (character models only)");
   const int Sp = round_up(S, 4);
   const long long need = 2ll * B * T * Sp + (long long)B * T + B;
   TS_REQUIRE(scratch_floats >= need, TS_ERR_INVALID, "ts_ctc_loss: scratch too small (need 2*B*T*Sp + B*T + B floats)");
@@ -226,10 +237,11 @@ extern "C" int ts_ctc_loss(const float* logits, int B, int V, int T, int pitch, 
   ctc::ctc_alpha_beta_kernel<<<B, 2 * ctc::ROLE_THREADS, smem1, st>>>(logits, V, T, pitch, in_len, targets, Lmax, tgt_len, blank,
                                                                       alpha, beta, Sp, lse, nll);
   TS_LAUNCH_CHECK("ctc_alpha_beta_kernel");
-  const size_t smem2 = (size_t)(V * (ctc::GT + 1) + Sp) * 4;
+  const size_t smem2 = (size_t)(ctc::CH * (ctc::GT + 1) + Sp) * 4;
   if (smem2 > 48 * 1024)
     TS_CUDA(cudaFuncSetAttribute(ctc::ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  dim3 grid(ceil_div(grad_pitch, ctc::GT), B);
+  TS_REQUIRE(B <= 65535 && ceil_div(V, ctc::CH) <= 65535, TS_ERR_UNSUPPORTED, "ts_ctc_loss: batch / vocabulary too large");
+  dim3 grid(ceil_div(grad_pitch, ctc::GT), B, ceil_div(V, ctc::CH));
   ctc::ctc_grad_kernel<<<grid, 256, smem2, st>>>(logits, V, Vp, T, pitch, grad_pitch, in_len, targets, Lmax, tgt_len, blank, alpha, beta, Sp,
                                                  lse, nll, gscale, B, loss, (__nv_bfloat16*)grad);
   TS_LAUNCH_CHECK("ctc_grad_kernel");
