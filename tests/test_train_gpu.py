@@ -562,3 +562,57 @@ def test_scatter_rows_is_the_transpose_of_gather_rows():
     exp[:, :, ::S] += sv
     assert np.abs(acc - exp).max() <= 2 ** -8 * np.abs(exp).max()
     assert np.array_equal(ops.unpack_rows(ops.gather_rows(up, T, S, None), Ts).cpu().numpy(), sv)
+
+
+def test_citrinet_model_training_step_vs_oracle():
+    """A whole (small) Citrinet -- stem, stride-1 / stride-2 blocks with SqueezeExcite, 640-wide head, 257-token vocabulary --
+    through CTCTrainStep: the loss equals the autograd torch port's, every parameter receives a gradient, the decoder-side
+    gradients agree, and a CUDA-graph step runs and lowers the loss."""
+    from oracle import ref_torch as RT
+    from thunder_speech_b200.citrinet.blocks import CitrinetEncoder
+
+    filters, kernels, strides, V = [64, 64, 64], [5, 7, 9], [1, 2, 1], 257
+    blist = synth.citrinet_block_list(filters, kernels, strides, 80)
+    st = synth.encoder_state(blist, seed=41, se=True)
+    dec = synth.decoder_state(640, V, seed=42)
+    x = synth.audio(6, 32000, 43, "noise")
+    lens = np.array([32000, 32000, 30000, 27000, 24000, 20000], np.int64)
+    rng = np.random.default_rng(44)
+    y = rng.integers(0, V - 1, (6, 10)).astype(np.int64)
+    y_len = rng.integers(3, 11, 6).astype(np.int64)
+    # oracle (fp32 autograd)
+    cfgs = R.citrinet_cfgs(filters, kernels, strides, feat_in=80)
+    stt = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st.items()}
+    for k, v in stt.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    dw_, db_ = torch.from_numpy(dec["weight"]).requires_grad_(True), torch.from_numpy(dec["bias"]).requires_grad_(True)
+    with torch.no_grad():
+        f, fl = RT.features(torch.from_numpy(x), torch.from_numpy(lens), nfilt=80)
+    e, el = RT.encoder(f, fl, cfgs, stt, train=True)
+    ref_loss = RT.ctc_loss(torch.nn.functional.conv1d(e, dw_, db_), torch.from_numpy(y), el, torch.from_numpy(y_len), V - 1)
+    ref_loss.backward()
+    # device
+    enc = CitrinetEncoder(filters, kernels, strides, feat_in=80)
+    enc.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    d = conv1d_decoder(640, V)
+    d.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()})
+    tokens = [f"t{i}" for i in range(V - 1)]
+    m = CTCModule(enc, d, FilterbankFeatures(nfilt=80, dither=0.0), BatchTextTransformer(tokens)).cuda()
+    m.encoder.train(); m.decoder.train()
+    step = CTCTrainStep(m, lr=1e-3, use_graph=False)
+    batch = (torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(y_len).cuda())
+    loss = step.loss_and_grads(*batch)
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    for k, p in list(m.encoder.named_parameters()) + list(m.decoder.named_parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float((p.grad ** 2).sum()) > 0, k
+    assert _cos(m.decoder.weight.grad.cpu().numpy(), dw_.grad.numpy()) > 0.99
+    assert _cos(m.decoder.bias.grad.cpu().numpy(), db_.grad.numpy()) > 0.99
+    last = max(int(k.split(".")[0]) for k in stt)
+    for k in stt:                                               # the head block: few layers of amplification
+        if k.startswith(f"{last}.") and stt[k].requires_grad:
+            assert _cos(dict(m.encoder.named_parameters())[k].grad.cpu().numpy(), stt[k].grad.numpy()) > 0.95, k
+    # graph-captured steps lower the loss
+    gstep = CTCTrainStep(m, lr=2e-3)
+    losses = [gstep.step(*batch).item() for _ in range(5)]
+    assert losses[-1] < 0.9 * losses[0], losses
