@@ -224,6 +224,13 @@ int ts_bn_bwd_apply_se(const void* dy, const void* z, const void* zr, const floa
                        int T, int pitch, int relu, void* dz, void* dzr, const float* mask_scale, const float* mask_shift,
                        const float* mask_scale_r, const float* mask_shift_r, const float* gate, const float* addc,
                        void* stream);
+/* torch.optim.AdamW's update for every parameter in ONE launch (BaseCTCModule's default optimizer, module.py:32,129-140).
+ * grad / exp_avg / exp_avg_sq: flat f32 buffers in the same element order; table: device array of n_entries rows of 4 int64
+ * {param pointer, offset in the flat buffers, elements, first tile} with 1024-element tiles.  bias_correction{1,2} =
+ * 1 - beta^step (the caller counts steps). */
+int ts_adamw(const long long* table, int n_entries, long long total_tiles, const float* grad, float* exp_avg,
+             float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+             float bias_correction2, void* stream);
 /* Prepares every weight operand of a training step from the fp32 master weights in ONE launch.  `table` is a device array
  * of n_entries rows of 8 int64: {src, dst, dstT, rows, cols, ldT, kind, first_tile}; tiles are 32 x 32 elements and
  * first_tile is the running sum of ceil(rows/32) * ceil(cols/32).  kind 0 (pointwise / decoder weight [rows, cols] f32):

@@ -616,3 +616,56 @@ def test_citrinet_model_training_step_vs_oracle():
     gstep = CTCTrainStep(m, lr=2e-3)
     losses = [gstep.step(*batch).item() for _ in range(5)]
     assert losses[-1] < 0.9 * losses[0], losses
+
+
+def test_fused_adamw_matches_torch_adamw():
+    """ts_adamw (one launch over all parameters) == torch.optim.AdamW with its default hyper-parameters, step for step."""
+    from thunder_speech_b200.parallel import flat_grad_views
+    from thunder_speech_b200.train import FusedAdamW
+
+    torch.manual_seed(3)
+    shapes = [(300, 17, 1), (5,), (129, 64), (1,), (1024, 33)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    flat = flat_grad_views(ours)
+    opt = FusedAdamW(ours, flat, lr=3e-3)
+    topt = torch.optim.AdamW(ref, lr=3e-3)
+    v0 = [p._version for p in ours]
+    for it in range(6):
+        for p, q in zip(ours, ref):
+            g = torch.randn_like(q) * (0.1 + it)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        opt.step()
+        topt.step()
+    for p, q in zip(ours, ref):
+        assert rel_err(p.detach().cpu().numpy(), q.detach().cpu().numpy())[0] < 2e-6
+    assert all(p._version > v for p, v in zip(ours, v0))           # caches keyed on _version see the update
+    sd = opt.state_dict()
+    opt2 = FusedAdamW(ours, flat, lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 6 and opt2.lr == 3e-3 and torch.equal(opt2.exp_avg, opt.exp_avg)
+
+
+def test_inference_after_training_uses_the_updated_weights_and_statistics():
+    """After CTCTrainStep.step() the eval()-mode forward must reflect the new parameters AND BatchNorm running statistics
+    (both are updated by kernels through raw pointers): compare with a freshly built model that loads the trained state_dict."""
+    case = _model_case()
+    m, step, batch = _device_model(case, lr=2e-3)
+    m.eval()
+    x = batch[0][:3]
+    before, _ = m(x, torch.full((3,), x.shape[1], device="cuda"))
+    m.encoder.train(); m.decoder.train()
+    for _ in range(3):
+        step.step(*batch)
+    m.eval()
+    after, _ = m(x, torch.full((3,), x.shape[1], device="cuda"))
+    assert not torch.equal(before, after)
+    filters, kernels = case[0], case[1]
+    enc = QuartznetEncoder(filters=filters, kernel_sizes=kernels, repeat_blocks=1)
+    enc.load_state_dict(m.encoder.state_dict(), strict=True)
+    d = conv1d_decoder(1024, 29)
+    d.load_state_dict(m.decoder.state_dict())
+    fresh = CTCModule(enc, d, FilterbankFeatures(nfilt=64, dither=0.0), BatchTextTransformer(synth.quartznet_vocab())).cuda().eval()
+    expect, _ = fresh(x, torch.full((3,), x.shape[1], device="cuda"))
+    assert torch.equal(after, expect)

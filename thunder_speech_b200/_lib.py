@@ -68,6 +68,8 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_bn_bwd_apply_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ts_adamw": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
+                         c_float, c_float, c_float, c_void_p]),
     "ts_prep_weights": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
     "ts_pw_gemm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p]),

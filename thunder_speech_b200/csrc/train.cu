@@ -806,3 +806,56 @@ extern "C" int ts_bn_bwd_apply_se(const void* dy, const void* z, const void* zr,
   TS_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TS_OK;
 }
+
+// ---- AdamW over every parameter of the model in ONE launch ------------------------------------------------------------
+// torch.optim.AdamW's update (decoupled weight decay, bias-corrected moments):
+//   p *= 1 - lr * wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// Gradients and both moments live in flat fp32 buffers (same element order); the parameters stay where the module keeps
+// them, addressed through a device table {param pointer, offset in the flat buffers, elements, first tile}; tiles are 1024
+// elements, a CTA finds its row by binary search (like prep_weights_kernel).
+namespace ts {
+namespace train {
+__global__ void __launch_bounds__(256)
+adamw_kernel(const long long* __restrict__ tab, int n, const float* __restrict__ grad, float* __restrict__ m,
+             float* __restrict__ v, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid * 4 + 3] <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const long long* e = tab + lo * 4;
+  float* p = reinterpret_cast<float*>(e[0]);
+  const long long off = e[1], cnt = e[2];
+  const long long i0 = ((long long)blockIdx.x - e[3]) * 1024 + threadIdx.x * 4;
+  const float decay = 1.f - lr * wd, step = lr / bc1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = i0 + j;
+    if (i < cnt) {
+      const float g = grad[off + i];
+      const float mi = b1 * m[off + i] + (1.f - b1) * g;
+      const float vi = b2 * v[off + i] + (1.f - b2) * g * g;
+      m[off + i] = mi;
+      v[off + i] = vi;
+      p[i] = p[i] * decay - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+  }
+}
+}  // namespace train
+}  // namespace ts
+
+extern "C" int ts_adamw(const long long* table, int n_entries, long long total_tiles, const float* grad, float* exp_avg,
+                        float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float bias_correction1, float bias_correction2, void* stream) {
+  TS_REQUIRE(table && grad && exp_avg && exp_avg_sq, TS_ERR_INVALID, "ts_adamw: null pointer");
+  TS_REQUIRE(n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), TS_ERR_INVALID, "ts_adamw: bad sizes");
+  TS_REQUIRE(bias_correction1 > 0.f && bias_correction2 > 0.f, TS_ERR_INVALID, "ts_adamw: bias corrections must be positive");
+  TS_CUDA(launch_pdl(train::adamw_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)stream,
+                     (option_pdl() & 2) != 0, table, n_entries, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
+                     bias_correction1, sqrtf(bias_correction2)));
+  TS_LAUNCH_CHECK("adamw_kernel");
+  return TS_OK;
+}

@@ -661,6 +661,64 @@ class EncoderTrainer:
             side.join()
 
 
+class FusedAdamW:
+    """``torch.optim.AdamW`` (the reference's default optimizer, module.py:32) as ONE kernel launch over every parameter
+    (``ts_adamw``): same update rule and defaults (lr 1e-3, betas (0.9, 0.999), eps 1e-8, weight_decay 1e-2).  Gradients are
+    read from the flat buffer the training step writes (``param.grad`` are views of it); both moments are flat buffers of
+    the same layout; the parameters stay where the module keeps them (device table of pointers, rebuilt if they move).
+    After the update the parameters' version counters are bumped so that caches keyed on ``_version`` (the folded inference
+    plans) notice the change."""
+
+    def __init__(self, params, flat_grad: Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2):
+        self.params = list(params)
+        self.flat = flat_grad
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.exp_avg = torch.zeros_like(flat_grad)
+        self.exp_avg_sq = torch.zeros_like(flat_grad)
+        self.step_count = 0
+        self._build()
+
+    def _build(self) -> None:
+        rows, off, tiles = [], 0, 0
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise TypeError("FusedAdamW: contiguous fp32 parameters expected")
+            n = p.numel()
+            rows.append([p.data_ptr(), off, n, tiles])
+            off += n
+            tiles += (n + 1023) // 1024
+        if off != self.flat.numel():
+            raise ValueError("FusedAdamW: the flat gradient buffer does not match the parameters")
+        self._ptrs = [r[0] for r in rows]
+        self.n, self.tiles = len(rows), tiles
+        self.table = torch.tensor(rows, dtype=torch.int64).to(self.flat.device)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Not needed by CTCTrainStep (the backward kernels overwrite every gradient); provided for API familiarity."""
+        self.flat.zero_()
+
+    def step(self) -> None:
+        if any(p.data_ptr() != q for p, q in zip(self.params, self._ptrs)):
+            self._build()
+        self.step_count += 1
+        b1, b2 = self.betas
+        _lib.check(_lib.lib().ts_adamw(_p(self.table), self.n, self.tiles, _p(self.flat), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                       self.lr, b1, b2, self.eps, self.weight_decay, 1.0 - b1 ** self.step_count,
+                                       1.0 - b2 ** self.step_count, _stream()), "ts_adamw")
+        torch.autograd.graph.increment_version(self.params)
+
+    def state_dict(self) -> Dict[str, object]:
+        return dict(step=self.step_count, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), lr=self.lr,
+                    betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+
+
 class _StepGraph:
     """One captured forward + loss + backward for fixed input shapes."""
 
@@ -690,7 +748,10 @@ class CTCTrainStep:
         if dev.type != "cuda":
             raise RuntimeError("CTCTrainStep runs on CUDA (sm_100a) modules only; there is no CPU fallback")
         self.flat = flat_grad_views(self.params)
-        self.opt = optimizer or torch.optim.AdamW(self.params, lr=lr, capturable=True, fused=True)
+        # default: AdamW like the reference (module.py:32), as one launch of this library; any torch optimizer over
+        # `self.params` can be passed instead
+        self.opt = optimizer or FusedAdamW(self.params, self.flat, lr=lr)
+        self._bn_buffers = [b for n_, b in list(module.encoder.named_buffers()) if "running_" in n_ or "num_batches" in n_]
         self.blank = blank_idx if blank_idx is not None else module.text_transform.vocab.blank_idx
         self.use_graph = use_graph
         self._graphs: Dict[tuple, _StepGraph] = {}
@@ -740,7 +801,9 @@ class CTCTrainStep:
     def loss_and_grads(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
         """Mean CTC loss (device scalar); parameter gradients are left in ``param.grad``."""
         if not self.use_graph:
-            return self._forward_backward(audio, lengths, y, y_lengths)
+            loss = self._forward_backward(audio, lengths, y, y_lengths)
+            self._bump_buffer_versions()
+            return loss
         if ensure_grad_views(self.params, self.flat):
             self._graphs.clear()          # the captured graphs wrote into gradient tensors that are no longer attached
         ptrs = tuple(p.data_ptr() for p in self.params)
@@ -757,7 +820,13 @@ class CTCTrainStep:
         g.y_len.copy_(y_lengths, non_blocking=True)
         g.graph.replay()
         g.replays += 1
+        self._bump_buffer_versions()
         return g.loss
+
+    def _bump_buffer_versions(self) -> None:
+        """The kernels update BatchNorm running statistics through raw pointers; tell torch (caches keyed on `_version`)."""
+        if self._bn_buffers:
+            torch.autograd.graph.increment_version(self._bn_buffers)
 
     def graph_launches(self) -> int:
         """Kernel launches of this library executed through graph replays so far (ts_launch_count only sees eager ones)."""
