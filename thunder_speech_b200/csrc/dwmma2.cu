@@ -169,7 +169,11 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   }
   if (warp >= 2) {
     // ===== Toeplitz blocks of this channel: Tq[r][j] = w[(64 q + j - 64 HL - r + P) / D], SW128 rows of 128 B =====
-    const float* wc = p.w + (size_t)c * p.K;
+    // the K taps of this channel are staged once in shared memory (borrowing the output staging buffer, which the epilogue
+    // first touches only after b_ready): the build below then needs no global loads
+    float* wc = reinterpret_cast<float*>(sO);
+    for (int k = tid - 64; k < p.K; k += THREADS - 64) wc[k] = __ldg(p.w + (size_t)c * p.K + k);
+    named_bar_sync(2, THREADS - 64);
     const int kd = p.K * p.D;
     for (int ci = tid - 64; ci < p.NQ * 64 * 8; ci += THREADS - 64) {
       const int q = ci >> 9, r = (ci >> 3) & 63, g = ci & 7;
