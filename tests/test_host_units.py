@@ -269,3 +269,32 @@ def test_vectorised_detokenisation_equals_reference_rules():
     cnt = torch.tensor([12, 0, 5, 1], dtype=torch.int32)
     tt = BatchTextTransformer(synth.quartznet_vocab())
     assert tt.decode_collapsed(col, cnt) == [slow(tt, col[b, :cnt[b]].numpy()) for b in range(4)]
+
+
+def test_text_encode_known_answers_and_tokenizers(tmp_path):
+    """BatchTextTransformer.encode with the reference's own known answer (tests/text/test_transforms.py:41-57), the
+    no-unknown-token filtering rule (vocab.py:77-80), a custom tokenizer and -- when the reference's sample model is around
+    -- sentencepiece pieces."""
+    from string import ascii_lowercase
+
+    from thunder_speech_b200.text_processing import word_tokenizer
+
+    tfm = BatchTextTransformer(tokens=[" "] + list(ascii_lowercase), blank_token="<blank>", pad_token="<blank>",
+                               unknown_token="<unk>", start_token="<bos>", end_token="<eos>")
+    encoded, lens = tfm.encode(["hello world", "oi"], return_length=True)
+    assert encoded.shape == (2, 13) and encoded.dtype == torch.long
+    assert encoded[0].tolist() == [29, 8, 5, 12, 12, 15, 0, 23, 15, 18, 12, 4, 30]
+    assert lens.tolist() == [13, 4]
+    assert encoded[1].tolist() == [29, 15, 9, 30] + [tfm.vocab.pad_idx] * 9
+    assert torch.equal(tfm.encode(["hello world", "oi"], return_length=False), encoded)
+    assert tfm.encode(["a!b"])[0].tolist() == [[29, 1, 28, 2, 30]]                     # unknown -> <unk>
+    plain = BatchTextTransformer(synth.quartznet_vocab())
+    y, yl = plain.encode(["ab!c", ""])
+    assert y.tolist() == [[1, 2, 3], [28, 28, 28]] and yl.tolist() == [3, 0]            # "!" dropped, pad = blank
+    words = BatchTextTransformer(["hello", "world"], custom_tokenizer_function=word_tokenizer)
+    assert words.encode(["hello there world"])[0].tolist() == [[0, 1]]
+    sp = "/root/reference/tests/nemo_config_samples/example_tokenizer.model"
+    if os.path.exists(sp):
+        bpe = BatchTextTransformer(["▁the", "s", "t", "▁ca"], sentencepiece_model=sp)
+        assert bpe.tokenizer("the cats") == ["▁the", "▁ca", "t", "s"]
+        assert bpe.encode(["the cats"])[0].tolist() == [[0, 3, 2, 1]]

@@ -669,3 +669,16 @@ def test_inference_after_training_uses_the_updated_weights_and_statistics():
     fresh = CTCModule(enc, d, FilterbankFeatures(nfilt=64, dither=0.0), BatchTextTransformer(synth.quartznet_vocab())).cuda().eval()
     expect, _ = fresh(x, torch.full((3,), x.shape[1], device="cuda"))
     assert torch.equal(after, expect)
+
+
+def test_training_step_takes_texts_like_the_reference():
+    """CTCTrainStep.training_step((audio, audio_lengths, texts)) == step() on the encoded labels (module.py:102-127)."""
+    case = _model_case()
+    m, step, batch = _device_model(case, lr=1e-3)
+    texts = ["hello world", "a test", "speech", "b two hundred", "x", "quartz net", "ctc", "gpu"]
+    y, yl = m.text_transform.encode(texts, device="cuda")
+    m2, step2, _ = _device_model(case, lr=1e-3)
+    l1 = step.training_step((batch[0], batch[1], texts))
+    l2_ = step2.step(batch[0], batch[1], y, yl)
+    assert torch.equal(l1, l2_) and torch.isfinite(l1)
+    assert torch.equal(m.decoder.weight, m2.decoder.weight)

@@ -27,8 +27,8 @@ def fix_vocab(vocab_tokens: List[str]) -> List[str]:
 def load_components_from_citrinet_config(config_path: Union[str, Path], sentencepiece_path: Union[str, Path] = None,
                                          augment_params: Dict = None) -> Tuple[nn.Module, nn.Module, BatchTextTransformer]:
     """(encoder, audio_transform, text_transform) from `model_config.yaml` (compatibility.py:54-110): the body is
-    `encoder.jasper[1:-1]` with per-block filters / kernel / stride.  The sentencepiece model is only needed to ENCODE text
-    (training targets), which is host-side string processing outside this package; decoding needs the token list alone."""
+    `encoder.jasper[1:-1]` with per-block filters / kernel / stride.  The sentencepiece model (when the file exists) is only used
+    to ENCODE training targets; decoding needs the token list alone."""
     augment_params = dict(augment_params or {})
     conf = load_yaml_config(config_path)
     body = conf["encoder"]["jasper"][1:-1]
@@ -50,7 +50,8 @@ def load_components_from_citrinet_config(config_path: Union[str, Path], sentence
     }
     labels = conf["labels"] if "labels" in conf else conf["decoder"]["vocabulary"]
     encoder = CitrinetEncoder(**encoder_cfg)
-    text_transform = BatchTextTransformer(tokens=fix_vocab(list(labels)))
+    sp = str(sentencepiece_path) if sentencepiece_path is not None and Path(sentencepiece_path).is_file() else None
+    text_transform = BatchTextTransformer(tokens=fix_vocab(list(labels)), sentencepiece_model=sp)
     audio_transform = FilterbankFeatures(**preprocess_cfg)
     return encoder, audio_transform, text_transform
 

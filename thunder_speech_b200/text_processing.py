@@ -1,18 +1,40 @@
-"""Greedy CTC detokenisation (the decode half of ``src/thunder/text_processing``).
-
-Only what ``BaseCTCModule.predict`` needs is here: the token table with the reference's special-token rules
-(``Vocabulary``, vocab.py:18-67,114-130) and ``BatchTextTransformer.decode_prediction``
-(transform.py:93-122).  Tokenisers / text encoding for training are host-side string processing outside the
-forward hot path.
+"""Text side of ``src/thunder/text_processing``: the token table with the reference's special-token rules
+(``Vocabulary``, vocab.py:18-130), greedy CTC detokenisation (``BatchTextTransformer.decode_prediction``,
+transform.py:93-122, what ``BaseCTCModule.predict`` needs) and label ENCODING for the training step
+(``encode``, transform.py:65-91: tokenise -> add start/end -> numericalise -> pad), with the reference's three
+tokenisers: characters (default), a sentencepiece model, or a custom function.  All host-side string processing.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Callable, List, Optional, Tuple, Union
 
 import numpy as np
 from torch import Tensor, nn
 
-__all__ = ["Vocabulary", "BatchTextTransformer"]
+__all__ = ["Vocabulary", "BatchTextTransformer", "BPETokenizer", "char_tokenizer", "word_tokenizer"]
+
+
+def char_tokenizer(text: str) -> List[str]:
+    """tokenizer.py:114-123."""
+    return list(text)
+
+
+def word_tokenizer(text: str) -> List[str]:
+    """tokenizer.py:102-111."""
+    return text.split()
+
+
+class BPETokenizer:
+    """sentencepiece pieces of a text (tokenizer.py:23-30)."""
+
+    def __init__(self, model_path: str):
+        import sentencepiece
+
+        self.tokenizer = sentencepiece.SentencePieceProcessor()
+        self.tokenizer.Load(model_path)
+
+    def __call__(self, text: str) -> List[str]:
+        return self.tokenizer.encode_as_pieces(text)
 
 
 class Vocabulary(nn.Module):
@@ -37,6 +59,24 @@ class Vocabulary(nn.Module):
         self.blank_idx = itos.index(self.blank_token)
         self.pad_idx = itos.index(self.pad_token)
 
+    def numericalize(self, tokens: List[str]) -> Tensor:
+        """vocab.py:68-84: without an unknown token, tokens outside the vocabulary are dropped; with one they map to it."""
+        import torch
+
+        if self.unknown_token is None:
+            tokens = [t for t in tokens if t in self.stoi]
+            return torch.tensor([self.stoi[t] for t in tokens], dtype=torch.long)
+        unk = self.stoi[self.unknown_token]
+        return torch.tensor([self.stoi.get(t, unk) for t in tokens], dtype=torch.long)
+
+    def add_special_tokens(self, tokens: List[str]) -> List[str]:
+        """vocab.py:98-112."""
+        if self.start_token is not None:
+            tokens = [self.start_token] + tokens
+        if self.end_token is not None:
+            tokens = tokens + [self.end_token]
+        return tokens
+
     def decode_into_text(self, indices) -> List[str]:
         return [self.itos[int(i)] for i in indices]
 
@@ -56,9 +96,24 @@ class BatchTextTransformer(nn.Module):
                  unknown_token: str = None, start_token: str = None, end_token: str = None,
                  sentencepiece_model: Optional[str] = None, custom_tokenizer_function=None):
         super().__init__()
-        if sentencepiece_model is not None or custom_tokenizer_function is not None:
-            raise NotImplementedError("tokenisers (text encoding for training) are outside the forward hot path")
         self.vocab = Vocabulary(tokens, blank_token, pad_token, unknown_token, start_token, end_token)
+        if custom_tokenizer_function:
+            self.tokenizer: Callable[[str], List[str]] = custom_tokenizer_function
+        elif sentencepiece_model:
+            self.tokenizer = BPETokenizer(str(sentencepiece_model))
+        else:
+            self.tokenizer = char_tokenizer
+
+    def encode(self, items: List[str], return_length: bool = True, device=None) -> Union[Tensor, Tuple[Tensor, Tensor]]:
+        """List of texts -> padded int64 ``[B, Lmax]`` (pad value ``pad_idx``) and lengths (transform.py:65-91)."""
+        import torch
+        from torch.nn.utils.rnn import pad_sequence
+
+        encoded = [self.vocab.numericalize(self.vocab.add_special_tokens(self.tokenizer(x))).to(device=device) for x in items]
+        batched = pad_sequence(encoded, batch_first=True, padding_value=self.vocab.pad_idx)
+        if return_length:
+            return batched, torch.tensor([len(it) for it in encoded], dtype=torch.long).to(device=device)
+        return batched
 
     @property
     def num_tokens(self) -> int:

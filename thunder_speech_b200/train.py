@@ -835,6 +835,13 @@ class CTCTrainStep:
     def allreduce_grads(self) -> None:
         allreduce_mean_(self.flat)
 
+    def training_step(self, batch, batch_idx: int = 0) -> Tensor:
+        """The reference's entry point (module.py:102-127): ``batch = (audio, audio_lengths, texts)``; the texts are encoded
+        with ``text_transform.encode`` on the host, then one optimisation step runs.  Returns the loss."""
+        audio, audio_lengths, texts = batch
+        y, y_lengths = self.m.text_transform.encode(texts, device=audio.device)
+        return self.step(audio, audio_lengths, y, y_lengths)
+
     def step(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
         loss = self.loss_and_grads(audio, lengths, y, y_lengths)
         self.allreduce_grads()
