@@ -10,7 +10,11 @@ Parity status: PINNED.  Every function below is checked (tests/test_oracle_golde
 outputs of the reference's own PyTorch modules run in the build container
 (``oracle/make_golden.py`` -> ``tests/golden/*.npz``), and against the exact known-answer cases of
 the reference test-suite (``tests/text/test_transforms.py:59-91``, ``tests/test_blocks.py:56-68``,
-``tests/quartznet/test_blocks_qn.py:89-143``).
+``tests/quartznet/test_blocks_qn.py:89-143``).  The rows added around the path are pinned the same way, each by its own
+generator importing the reference's code: audio ingest / resampling (``oracle/make_golden_ingest.py`` ->
+``tests/golden/ingest.npz``, torchaudio 0.12's ``resample``), SpecAugment / SpecCutout under fixed seeds
+(``oracle/make_golden_augment.py`` -> ``augment.npz``); the training-step oracle is ``oracle/ref_torch.py`` (autograd) pinned
+by ``oracle/make_golden_train.py`` -> ``train.npz``.
 
 The reference's arithmetic lives in third-party libraries that are not part of the reference tree:
 PyTorch (pinned ``torch 1.12.0``, ``poetry.lock:1050``) for ``torch.stft``/``conv1d``/``batch_norm``
