@@ -450,7 +450,15 @@ class BlockTrainer:
         return ent
 
     # -- forward ---------------------------------------------------------------------------------------
-    def forward(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool, update_running: bool = True):
+    def _nbt_buffers(self) -> List[Tensor]:
+        nbt = [sb.bn.num_batches_tracked for sb in self.subs if sb.bn.track_running_stats]
+        if self.res is not None and self.res[1].track_running_stats:
+            nbt.append(self.res[1].num_batches_tracked)
+        return nbt
+
+    def forward(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool, update_running: bool = True,
+                bump_nbt: bool = True):
+        """``bump_nbt=False``: the caller increments ``num_batches_tracked`` for all blocks at once (EncoderTrainer)."""
         if self.pack is None:            # stand-alone use (block-level tests): own pack, refreshed every forward
             self.pack, self._own_pack = WeightPack(self.pack_entries()), True
         if self._own_pack:
@@ -517,10 +525,8 @@ class BlockTrainer:
             rec["y"] = y
             tape["subs"].append(rec)
             cur, Tc, lc = y, Ta, la
-        if update_running:
-            nbt = [sb.bn.num_batches_tracked for sb in self.subs if sb.bn.track_running_stats]
-            if self.res is not None and self.res[1].track_running_stats:
-                nbt.append(self.res[1].num_batches_tracked)
+        if update_running and bump_nbt:
+            nbt = self._nbt_buffers()
             if nbt:
                 torch._foreach_add_(nbt, 1)
         return y, Tc, lc, tape
@@ -646,8 +652,12 @@ class EncoderTrainer:
         tapes = []
         for i, bt in enumerate(self.blocks):
             rows, T, lens, tape = bt.forward(rows, T, lens, zero_tail=(i != len(self.blocks) - 1),
-                                             update_running=update_running)
+                                             update_running=update_running, bump_nbt=False)
             tapes.append(tape)
+        if update_running:   # nn.BatchNorm1d bookkeeping for every layer of the model in one multi-tensor launch
+            nbt = [b for bt in self.blocks for b in bt._nbt_buffers()]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
         return rows, T, lens, tapes
 
     def backward(self, tapes, dy: Tensor, side: Optional[_SideStream] = None) -> None:
