@@ -17,7 +17,7 @@ from torch import Tensor, nn
 
 from ..blocks import Masked
 
-__all__ = ["FeatureBatchNormalizer", "DitherAudio", "PreEmphasisFilter", "PowerSpectrum", "MelScale",
+__all__ = ["patch_stft", "FeatureBatchNormalizer", "DitherAudio", "PreEmphasisFilter", "PowerSpectrum", "MelScale",
            "FilterbankFeatures", "mel_filterbank"]
 
 
@@ -233,3 +233,13 @@ def FilterbankFeatures(
         augment.append(SpecAugment(time_masks=num_time_masks, freq_masks=num_freq_masks, time_width=mask_time_width,
                                    freq_width=mask_freq_width))
     return _FusedFilterbank(dither, preemph, n_window_size, n_window_stride, n_fft, sample_rate, nfilt, augment)
+
+
+def patch_stft(filterbank: nn.Module) -> nn.Module:
+    """API counterpart of the reference's ``patch_stft`` (transform.py:324-336), which swaps ``torch.stft`` for a
+    convolution-based DFT so that the front-end can be exported to ONNX / run on mobile CPUs.  Here the spectrum never goes
+    through ``torch.stft`` -- the fused kernel computes it -- so there is nothing to patch: the filterbank is returned
+    unchanged (its outputs are, trivially, identical before and after, which is what the reference's test
+    ``tests/quartznet/test_transform_qn.py:286-295`` asserts at atol 1e-3).  Export goes through
+    ``CTCModule.to_torchscript`` (custom ops), not ONNX."""
+    return filterbank
