@@ -176,3 +176,54 @@ def test_to_torchscript_trace_roundtrip(tmp_path):
     o3, _ = loaded(x3, l3)
     r3, _ = m(x3, l3)
     assert torch.equal(o3, r3)
+
+
+def test_random_block_configurations_vs_oracle():
+    """The reference's property test over random block configurations (tests/quartznet/test_blocks_qn.py:158-184,
+    tests/citrinet/test_blocks_cn.py:52-137: shape / length laws for random Cin, Cout, repeat, K, stride, dilation,
+    residual) -- here against the numpy oracle's VALUES, for both block kinds, eval mode, ragged lengths."""
+    import numpy as np
+    import torch
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from oracle import ref_numpy as R
+    from thunder_speech_b200 import ops, synth
+    from thunder_speech_b200.citrinet.blocks import CitrinetBlock
+    from thunder_speech_b200.quartznet.blocks import QuartznetBlock
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(kind=st.sampled_from(["quartznet", "citrinet"]), cin=st.sampled_from([8, 16, 40, 64, 136]),
+           cout=st.sampled_from([8, 24, 64, 144, 256]), rep=st.integers(1, 4), K=st.sampled_from([1, 3, 5, 11, 33]),
+           stride=st.sampled_from([1, 1, 2]), dil=st.sampled_from([1, 1, 2]), res=st.booleans(), B=st.integers(1, 4),
+           T=st.integers(20, 260), seed=st.integers(0, 1000))
+    def check(kind, cin, cout, rep, K, stride, dil, res, B, T, seed):
+        if stride > 1 and dil > 1:
+            with pytest.raises(ValueError):                                  # quartznet/blocks.py:192-193
+                QuartznetBlock(cin, cout, repeat=rep, kernel_size=(K,), stride=(stride,), dilation=(dil,), residual=res,
+                               separable=True)
+            return
+        if kind == "quartznet" and stride > 1 and res:
+            return        # residual stride = stride**repeat: lengths only agree for repeat == 1 in the reference too
+        rng = np.random.Generator(np.random.PCG64(seed))
+        se = kind == "citrinet"
+        stt = synth.block_state(rng, "", cin, cout, rep, K, res, True, se=se)
+        x = rng.standard_normal((B, cin, T)).astype(np.float32)
+        lens = np.sort(rng.integers(max(T // 2, 1), T + 1, B))[::-1].astype(np.int64).copy()
+        lens[0] = T
+        cfg = R.BlockCfg(cin, cout, repeat=rep, kernel_size=K, stride=stride, dilation=dil, residual=res, separable=True,
+                         kind=kind)
+        ref, ref_len = R.block_forward(np.where(np.arange(T)[None, None, :] < lens[:, None, None], x, 0).astype(np.float32),
+                                       lens, cfg, stt, "")
+        cls = QuartznetBlock if kind == "quartznet" else CitrinetBlock
+        blk = cls(cin, cout, repeat=rep, kernel_size=(K,), stride=(stride,), dilation=(dil,), residual=res, separable=True)
+        blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in stt.items()}, strict=True)
+        blk = blk.cuda().eval()
+        y, yl = blk(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda())
+        assert tuple(y.shape) == ref.shape and np.array_equal(yl.cpu().numpy(), ref_len)
+        m = np.arange(ref.shape[-1])[None, None, :] < ref_len[:, None, None]
+        got = y.float().cpu().numpy()
+        err = np.abs(np.where(m, got - ref, 0)).max() / max(np.abs(ref).max(), 1e-6)
+        assert err < 2e-2, (kind, cin, cout, rep, K, stride, dil, res, B, T, err)
+
+    check()
