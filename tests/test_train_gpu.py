@@ -682,3 +682,61 @@ def test_training_step_takes_texts_like_the_reference():
     l2_ = step2.step(batch[0], batch[1], y, yl)
     assert torch.equal(l1, l2_) and torch.isfinite(l1)
     assert torch.equal(m.decoder.weight, m2.decoder.weight)
+
+
+def test_random_block_configurations_training_vs_oracle():
+    """Random block configurations through BlockTrainer (forward, dx, every parameter gradient) against the autograd torch
+    port with bf16 storage simulated: odd channel counts (the <= 128-row GEMM kernel, partial tiles), K = 1 .. 33, dilation 2,
+    stride-2 Citrinet blocks, with / without residual and SqueezeExcite -- the fallback kernels get the same scrutiny as the
+    QuartzNet-15x5 shapes."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from oracle import ref_torch as RT
+    from thunder_speech_b200.citrinet.blocks import CitrinetBlock
+
+    @settings(max_examples=16, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(kind=st.sampled_from(["quartznet", "citrinet"]), cin=st.sampled_from([8, 16, 40, 64, 136]),
+           cout=st.sampled_from([8, 24, 64, 144, 256]), rep=st.integers(1, 3), K=st.sampled_from([1, 3, 5, 11, 33]),
+           stride=st.sampled_from([1, 1, 2]), dil=st.sampled_from([1, 1, 2]), res=st.booleans(), B=st.integers(2, 5),
+           T=st.integers(40, 200), seed=st.integers(0, 1000))
+    def check(kind, cin, cout, rep, K, stride, dil, res, B, T, seed):
+        if stride > 1 and (dil > 1 or kind == "quartznet"):
+            return     # QuartzNet strides every sub-block (only its stem, which needs no dx); stride with dilation is a ValueError
+        rng = np.random.Generator(np.random.PCG64(seed))
+        se = kind == "citrinet"
+        st_ = synth.block_state(rng, "", cin, cout, rep, K, res, True, se=se)
+        x = np.maximum(rng.standard_normal((B, cin, T)), 0).astype(np.float32)
+        lens = np.sort(rng.integers(T // 2, T + 1, B))[::-1].astype(np.int64).copy()
+        lens[0] = T
+        To = (T - 1) // stride + 1
+        lo_ref = (lens - 1) // stride + 1
+        m = (np.arange(T)[None, :] < lens[:, None])[:, None, :]
+        mo = (np.arange(To)[None, :] < lo_ref[:, None])[:, None, :]
+        Rm = np.where(mo, rng.standard_normal((B, cout, To)), 0).astype(np.float32)
+        cfg = R.BlockCfg(cin, cout, repeat=rep, kernel_size=K, stride=stride, dilation=dil, residual=res, separable=True,
+                         kind=kind)
+        sd = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in st_.items()}
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and "running" not in k:
+                v.requires_grad_(True)
+        xt = torch.from_numpy(np.where(m, x, 0).astype(np.float32)).requires_grad_(True)
+        y, yl = RT.block(xt, torch.from_numpy(lens), cfg, sd, "", train=True, store=RT.bf16_store)
+        (y * torch.from_numpy(Rm)).sum().backward()
+        cls = QuartznetBlock if kind == "quartznet" else CitrinetBlock
+        blk = cls(cin, cout, repeat=rep, kernel_size=(K,), stride=(stride,), dilation=(dil,), residual=res, separable=True)
+        blk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st_.items()}, strict=True)
+        blk = blk.cuda().train()
+        bt = BlockTrainer(blk)
+        l32 = torch.from_numpy(lens.astype(np.int32)).cuda()
+        yy, T_out, lo, tape = bt.forward(ops.pack_rows(torch.from_numpy(x).cuda(), l32), T, l32, zero_tail=True)
+        tag = (kind, cin, cout, rep, K, stride, dil, res, B, T, seed)
+        assert T_out == To and np.array_equal(lo.cpu().numpy(), lo_ref), tag
+        assert l2(ops.unpack_rows(yy, T_out).cpu().numpy(), np.where(mo, y.detach().numpy(), 0)) < 8e-3, tag
+        dx = bt.backward(tape, ops.pack_rows(torch.from_numpy(Rm).cuda()), need_dx=True)
+        assert l2(ops.unpack_rows(dx, T).cpu().numpy(), xt.grad.numpy()) < 3e-2, tag
+        for k, p in blk.named_parameters():
+            e = l2(p.grad.cpu().numpy(), sd[k].grad.numpy())
+            assert e < 3e-2, tag + (k, e)
+
+    check()
