@@ -17,6 +17,7 @@ over batch slices of the deterministic partial reductions.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -386,15 +387,20 @@ class _SideStream:
         self.keep: List[Tensor] = []
         self.dirty = False
 
-    def run(self, fn, *tensors: Tensor) -> None:
+    def run(self, fn, *tensors: Tensor) -> "torch.cuda.Event":
+        """Runs ``fn`` on the side stream after everything queued so far on the current stream; returns the event that marks
+        its completion (wait on it before consuming results on the main stream, or call ``join``)."""
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
         self.keep.extend(t for t in tensors if t is not None)
+        done = torch.cuda.Event()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
             fn()
+            done.record(self.stream)
         self.dirty = True
+        return done
 
     def join(self) -> None:
         if self.dirty:
@@ -457,8 +463,10 @@ class BlockTrainer:
         return nbt
 
     def forward(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool, update_running: bool = True,
-                bump_nbt: bool = True):
-        """``bump_nbt=False``: the caller increments ``num_batches_tracked`` for all blocks at once (EncoderTrainer)."""
+                bump_nbt: bool = True, side: Optional[_SideStream] = None):
+        """``bump_nbt=False``: the caller increments ``num_batches_tracked`` for all blocks at once (EncoderTrainer).
+        ``side``: run the residual branch's GEMM (it only depends on the block input) on this forked stream, in parallel with
+        the main chain of sub-blocks; joined before the last BatchNorm apply."""
         if self.pack is None:            # stand-alone use (block-level tests): own pack, refreshed every forward
             self.pack, self._own_pack = WeightPack(self.pack_entries()), True
         if self._own_pack:
@@ -470,6 +478,19 @@ class BlockTrainer:
             xr_in = ops.gather_rows(x, T, self.res_stride, lens)
             Tr = (T - 1) // self.res_stride + 1
         tape.update(xr=xr_in, Tr=Tr)
+        res_out, res_done = {}, None
+        if self.res is not None and side is not None:
+            def _res_branch():
+                res_out["z"], res_out["st"] = pw_gemm_stats(self.pack.get(self.res[0].weight)[0], xr_in, Tr)
+            res_done = side.run(_res_branch, xr_in)
+
+        def residual_gemm():
+            """(zr, partial stats) of the residual 1x1 conv: from the side stream if it was forked, else computed here."""
+            if res_done is not None:
+                torch.cuda.current_stream().wait_event(res_done)
+                return res_out["z"], res_out["st"]
+            return pw_gemm_stats(self.pack.get(self.res[0].weight)[0], xr_in, Tr)
+
         cur, Tc, lc = x, T, lens
         B = x.shape[0]
         n = len(self.subs)
@@ -503,7 +524,7 @@ class BlockTrainer:
                     rconv, rbn = self.res
                     if Tr != Ta:
                         raise ValueError(f"residual branch length {Tr} != main branch length {Ta}")
-                    zr, zrst = pw_gemm_stats(self.pack.get(rconv.weight)[0], xr_in, Tr)
+                    zr, zrst = residual_gemm()
                     sc_r, sh_r, mean_r, inv_r = bn_finalize(zrst, B * Tr, rbn, update_running)
                     st_r = torch.stack([sc_r, sh_r, mean_r, inv_r])
                 y = bn_apply_se(z, scale, shift, zr, sc_r, sh_r, gate, Ta, la if zero_tail else None, True)
@@ -511,10 +532,9 @@ class BlockTrainer:
                            rowsum=rowsum)
             elif last and self.res is not None:
                 rconv, rbn = self.res
-                wr = self.pack.get(rconv.weight)[0]
                 if Tr != Ta:
                     raise ValueError(f"residual branch length {Tr} != main branch length {Ta}")
-                zr, zrst = pw_gemm_stats(wr, xr_in, Tr)
+                zr, zrst = residual_gemm()
                 y, st, st_r = bn_apply_fused(z, zst, sb.bn, zr, zrst, rbn, Ta, la if zero_tail else None, True,
                                              update_running)
                 rec.update(zr=zr, stats=st, stats_r=st_r)
@@ -649,11 +669,14 @@ class EncoderTrainer:
         if self.pack is None:
             self.build_pack()
         self.pack.refresh()
+        side = _SideStream(rows.device) if os.environ.get("THUNDER_B200_FWD_SIDE", "1") != "0" else None
         tapes = []
         for i, bt in enumerate(self.blocks):
             rows, T, lens, tape = bt.forward(rows, T, lens, zero_tail=(i != len(self.blocks) - 1),
-                                             update_running=update_running, bump_nbt=False)
+                                             update_running=update_running, bump_nbt=False, side=side)
             tapes.append(tape)
+        if side is not None:
+            side.join()
         if update_running:   # nn.BatchNorm1d bookkeeping for every layer of the model in one multi-tensor launch
             nbt = [b for bt in self.blocks for b in bt._nbt_buffers()]
             if nbt:
