@@ -807,13 +807,20 @@ class CTCTrainStep:
             logits = ops.pw_gemm(wd, rows, None, None, T, dec.bias.detach(), None, True, False, None, None, None)
             loss_b, dlogits = ctc_loss(logits, T, l32o, y, y_lengths.to(torch.int64), self.blank, Vp)
             loss = loss_b.mean()
-            # decoder gradients: dW_d = dlogits enc^T, db = sum dlogits, d enc = W_d^T dlogits
-            dwd = pw_wgrad(dlogits, rows, T)
-            _grad(dec.weight).copy_(dwd[:V].view_as(dec.weight))
-            if dec.bias is not None:
-                _grad(dec.bias).copy_(row_stats_partial(dlogits, T).sum(0)[:V, 0])
+            # decoder gradients: d enc = W_d^T dlogits is on the critical path; dW_d = dlogits enc^T and db = sum dlogits run
+            # on the forked stream together with the encoder's weight gradients
+            side = _SideStream(rows.device)
+
+            def _decoder_param_grads():
+                dwd = pw_wgrad(dlogits, rows, T)
+                _grad(dec.weight).copy_(dwd[:V].view_as(dec.weight))
+                if dec.bias is not None:
+                    _grad(dec.bias).copy_(row_stats_partial(dlogits, T).sum(0)[:V, 0])
+
+            side.run(_decoder_param_grads, dlogits, rows)
             d_enc = ops.pw_gemm(wdT, dlogits, None, None, T, None, None, False, False, None, None, None)
-            self.enc.backward(tapes, d_enc)
+            self.enc.backward(tapes, d_enc, side=side)
+            side.join()
         return loss
 
     def _capture(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> _StepGraph:
