@@ -298,3 +298,23 @@ def test_text_encode_known_answers_and_tokenizers(tmp_path):
         bpe = BatchTextTransformer(["▁the", "s", "t", "▁ca"], sentencepiece_model=sp)
         assert bpe.tokenizer("the cats") == ["▁the", "▁ca", "t", "s"]
         assert bpe.encode(["the cats"])[0].tolist() == [[0, 3, 2, 1]]
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under the package imports it, and ``bench.py`` only does so inside
+    its CPU-baseline function.  Nothing that runs on the GPU box reads /root/reference."""
+    pkg = os.path.join(ROOT, "thunder_speech_b200")
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+                assert not pat.search(src), f"{fn} imports the oracle"
+                assert "/root/reference" not in src, f"{fn} reads the reference tree"
+    bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    hits = [m.start() for m in pat.finditer(bench)]
+    assert hits, "bench.py must time the oracle port as its cpu_baseline"
+    start = bench.index("def cpu_port_rate")
+    end = bench.index("\ndef ", start + 1)
+    assert all(start < h < end for h in hits), "oracle imported outside bench.py cpu_port_rate()"
+    assert "/root/reference" not in bench
