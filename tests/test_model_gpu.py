@@ -143,13 +143,20 @@ def test_batch_independence():
     assert torch.equal(full[1:2], solo)
 
 
-def test_predict_stream_matches_predict():
-    """The pipelined serving loop (H2D / compute / D2H overlapped) returns the same strings as predict()."""
+@pytest.mark.parametrize("depth,nbatch", [(2, 5), (3, 7), (3, 2), (4, 1)])
+def test_predict_stream_matches_predict(depth, nbatch):
+    """The pipelined serving loop (H2D / compute / D2H overlapped, `depth` batches in flight, also fewer batches than
+    the pipeline is deep) returns the same strings as predict(), in order."""
     m, _ = build_qn5x5()
-    xs = [torch.from_numpy(synth.audio(2, 9000, 40 + i, "tones")).pin_memory() for i in range(5)]
+    xs = [torch.from_numpy(synth.audio(2, 9000, 40 + i, "tones")).pin_memory() for i in range(nbatch)]
     want = [m.predict(x.cuda()) for x in xs]
-    got = list(m.predict_stream(xs))
+    got = list(m.predict_stream(xs, depth=depth))
     assert got == want
+    # a second stream of the same shape reuses the cached staging buffers; an abandoned stream must not leak into it
+    it = m.predict_stream(xs, depth=depth)
+    assert next(it) == want[0]
+    del it
+    assert list(m.predict_stream(list(reversed(xs)), depth=depth)) == list(reversed(want))
 
 
 def test_to_torchscript_trace_roundtrip(tmp_path):

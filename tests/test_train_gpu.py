@@ -684,6 +684,22 @@ def test_training_step_takes_texts_like_the_reference():
     assert torch.equal(m.decoder.weight, m2.decoder.weight)
 
 
+def test_fit_stream_equals_step_by_step():
+    """CTCTrainStep.fit_stream (pinned host batches, copies on a side stream, loss read back one step late) produces the
+    same losses and the same weights as calling step() on device tensors, for pipeline depths 1-3."""
+    case = _model_case()
+    m0, step0, batch = _device_model(case, lr=1e-3)
+    want = [float(step0.step(*batch)) for _ in range(4)]
+    host = tuple(t.cpu().pin_memory() for t in batch)
+    for depth in (1, 2, 3):
+        m, step, _ = _device_model(case, lr=1e-3)
+        got = list(step.fit_stream((host for _ in range(4)), depth=depth))
+        assert got == want, (depth, got, want)
+        sd0 = m0.state_dict()
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, sd0[k]), (depth, k)
+
+
 def test_random_block_configurations_training_vs_oracle():
     """Random block configurations through BlockTrainer (forward, dx, every parameter gradient) against the autograd torch
     port with bf16 storage simulated: odd channel counts (the <= 128-row GEMM kernel, partial tiles), K = 1 .. 33, dilation 2,

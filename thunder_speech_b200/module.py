@@ -32,6 +32,7 @@ class CTCModule(nn.Module):
         self.encoder_final_dimension = encoder_final_dimension
         self._dec_cache = None
         self._graphs: Dict[Tuple[int, int], "_PredictGraph"] = {}
+        self._pipes: Dict[tuple, "_StreamPipe"] = {}
 
     # -- decoder parameters as GEMM operands ----------------------------------------------------
     def _decoder_operands(self) -> Tuple[Tensor, Tensor]:
@@ -118,44 +119,60 @@ class CTCModule(nn.Module):
             torch.jit.save(traced, file_path)
         return traced
 
-    def predict_stream(self, batches: Iterable[Tensor]) -> Iterator[List[str]]:
+    def predict_stream(self, batches: Iterable[Tensor], depth: int = 3) -> Iterator[List[str]]:
         """Serving loop over HOST batches ``[B, N]`` of one fixed shape (pinned memory for true overlap): the
-        host-to-device copy of batch i+1 runs on a copy stream while batch i computes (CUDA-graph replay), and the
-        detokenisation of batch i-1 runs on the CPU meanwhile.  Yields one ``List[str]`` per batch, in order."""
+        host-to-device copies run on a copy stream ahead of the compute (CUDA-graph replay) and the detokenisation of
+        finished batches runs on the CPU meanwhile.  ``depth`` batches are in flight: with 3 the copy of batch i+1 is
+        queued before the host waits for batch i-1, so it has a whole step to finish even when the PCIe transfer takes
+        almost as long as the compute (with 2 it only starts after batch i-1 was detokenised).  Yields one
+        ``List[str]`` per batch, in order."""
+        depth = max(2, int(depth))
         pipe = None
         pending = []
         for i, xb in enumerate(batches):
             if pipe is None:
-                pipe = _StreamPipe(self, xb)
+                # staging buffers, pinned result buffers and the captured graph are kept per (shape, depth): building
+                # them costs ~20 ms (cudaHostAlloc, graph warm-up), which a short stream would pay on every call
+                key = (tuple(xb.shape), depth)
+                pipe = self._pipes.get(key)
+                if pipe is None:
+                    pipe = self._pipes[key] = _StreamPipe(self, xb, depth)
+                pipe.reset()
             pending.append(pipe.submit(i, xb))
-            if len(pending) == 2:
+            if len(pending) == depth:
                 yield pipe.collect(pending.pop(0))
         while pending:
             yield pipe.collect(pending.pop(0))
 
 
 class _StreamPipe:
-    """Double-buffered H2D / compute / D2H pipeline behind :meth:`CTCModule.predict_stream`."""
+    """Multi-buffered H2D / compute / D2H pipeline behind :meth:`CTCModule.predict_stream`."""
 
-    def __init__(self, module: CTCModule, example: Tensor):
+    def __init__(self, module: CTCModule, example: Tensor, depth: int = 3):
         self.m = module
+        self.depth = depth
         dev = next(module.encoder.parameters()).device
         B, N = example.shape
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.stage = [torch.empty((B, N), device=dev, dtype=torch.float32) for _ in range(2)]
-        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
-        self.stage_free = [torch.cuda.Event() for _ in range(2)]
-        self.d2h_done = [torch.cuda.Event() for _ in range(2)]
+        self.stage = [torch.empty((B, N), device=dev, dtype=torch.float32) for _ in range(depth)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        self.stage_free = [torch.cuda.Event() for _ in range(depth)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(depth)]
         _, col, cnt = module.predict_ids_graphed(self.stage[0])   # builds / warms the graph for this shape
         torch.cuda.synchronize(dev)
-        self.host_col = [torch.empty(col.shape, dtype=col.dtype).pin_memory() for _ in range(2)]
-        self.host_cnt = [torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory() for _ in range(2)]
+        self.host_col = [torch.empty(col.shape, dtype=col.dtype).pin_memory() for _ in range(depth)]
+        self.host_cnt = [torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory() for _ in range(depth)]
+
+    def reset(self) -> None:
+        """Start of a new stream over the same buffers: nothing of the previous one may still be in flight."""
+        torch.cuda.current_stream().synchronize()
+        self.copy_stream.synchronize()
 
     def submit(self, i: int, xb: Tensor) -> int:
-        s = i % 2
+        s = i % self.depth
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
-            if i >= 2:
+            if i >= self.depth:
                 self.copy_stream.wait_event(self.stage_free[s])
             self.stage[s].copy_(xb, non_blocking=True)
             self.h2d_done[s].record(self.copy_stream)

@@ -887,3 +887,43 @@ class CTCTrainStep:
         self.allreduce_grads()
         self.opt.step()
         return loss
+
+    def fit_stream(self, batches, depth: int = 2):
+        """Training loop over HOST batches ``(audio, audio_lengths, y, y_lengths)`` of one fixed shape (pinned memory for
+        true overlap) -- what Lightning's loop does around ``training_step`` (module.py:102-127) with a pinned-memory
+        DataLoader: the host->device copies of batch i+1 run on a copy stream while step i computes, and the loss of
+        step i is read back through pinned memory ``depth - 1`` steps late, so the host never idles the GPU.  Every step
+        still copies its own inputs in and its own loss out.  Yields one float loss per step, in order."""
+        depth = max(1, int(depth))
+        dev = self.params[0].device
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage, host_loss = None, None
+        h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        slot_free = [torch.cuda.Event() for _ in range(depth)]
+        done = [torch.cuda.Event() for _ in range(depth)]
+        pending = []
+        for i, batch in enumerate(batches):
+            if stage is None:
+                stage = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch] for _ in range(depth)]
+                host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(depth)]
+            s = i % depth
+            cur = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_stream):
+                if i >= depth:
+                    copy_stream.wait_event(slot_free[s])
+                for d, h in zip(stage[s], batch):
+                    d.copy_(h, non_blocking=True)
+                h2d_done[s].record(copy_stream)
+            cur.wait_event(h2d_done[s])
+            loss = self.step(*stage[s])
+            slot_free[s].record(cur)
+            host_loss[s].copy_(loss, non_blocking=True)
+            done[s].record(cur)
+            pending.append(s)
+            if len(pending) == depth:
+                j = pending.pop(0)
+                done[j].synchronize()
+                yield float(host_loss[j])
+        for j in pending:
+            done[j].synchronize()
+            yield float(host_loss[j])
