@@ -684,6 +684,47 @@ def test_training_step_takes_texts_like_the_reference():
     assert torch.equal(m.decoder.weight, m2.decoder.weight)
 
 
+def test_training_step_is_an_autograd_node_like_the_reference():
+    """CTCModule.training_step(batch) returns a loss with a grad_fn; loss.backward() ACCUMULATES the kernel gradients into
+    param.grad exactly like torch autograd would (Lightning's automatic optimisation: backward, optimizer.step,
+    zero_grad(set_to_none=True)); a stock torch.optim.AdamW then moves the weights like the fused AdamW kernel does."""
+    case = _model_case()
+    texts = ["hello world", "a test", "speech", "b two hundred", "x", "quartz net", "ctc", "gpu"]
+    m1, step1, batch = _device_model(case, lr=1e-3)
+    y, yl = m1.text_transform.encode(texts, device="cuda")
+    want_loss = step1.loss_and_grads(batch[0], batch[1], y, yl).clone()
+    want = step1.flat.clone()
+    m2, _, _ = _device_model(case, lr=1e-3)
+    params = list(m2.encoder.parameters()) + list(m2.decoder.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    loss = m2.training_step((batch[0], batch[1], texts), 0)
+    assert loss.requires_grad and loss.grad_fn is not None and torch.equal(loss.detach(), want_loss)
+    loss.backward()
+    got = torch.cat([p.grad.reshape(-1) for p in params])
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+    # second micro-batch without zero_grad: gradients accumulate (same weights, deterministic kernels -> exactly 2 g)
+    (m2.training_step((batch[0], batch[1], texts), 1) * 0.5).backward()
+    got = torch.cat([p.grad.reshape(-1) for p in params])
+    assert torch.allclose(got, 1.5 * want, rtol=1e-6, atol=0)
+    # Lightning's default zero_grad drops the grads; the next backward starts from zero again
+    opt.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in params)
+    m2.training_step((batch[0], batch[1], texts), 2).backward()
+    got = torch.cat([p.grad.reshape(-1) for p in params])
+    assert torch.equal(got, want)
+    graphs = len(m2.__dict__["_b200_step"]._graphs)
+    assert graphs == 1                               # re-attaching the gradient views did not force a re-capture
+    opt.step()
+    step1.opt.step()
+    for (k, a), (_, b) in zip(m2.named_parameters(), m1.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), k
+    # and the updated weights are what the next step trains on
+    l3 = m2.training_step((batch[0], batch[1], texts), 3)
+    assert torch.isfinite(l3) and float(l3.detach()) != float(want_loss)
+
+
 def test_fit_stream_equals_step_by_step():
     """CTCTrainStep.fit_stream (pinned host batches, copies on a side stream, loss read back one step late) produces the
     same losses and the same weights as calling step() on device tensors, for pipeline depths 1-3."""

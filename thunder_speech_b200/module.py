@@ -91,6 +91,21 @@ class CTCModule(nn.Module):
             self._graphs[key] = g
         return g.replay(x)
 
+    def training_step(self, batch, batch_idx: int = 0) -> Tensor:
+        """``BaseCTCModule.training_step`` (src/thunder/module.py:102-127): ``batch = (audio, audio_lengths, texts)`` -> mean
+        CTC loss.  The returned scalar is connected to torch's autograd graph: ``loss.backward()`` (what Lightning's
+        automatic optimisation calls next) delivers the kernel-computed gradients to ``param.grad`` of every encoder /
+        decoder parameter, so any torch optimizer / LR scheduler / gradient-clipping hook keeps working.  The explicit,
+        faster loop (single-launch AdamW, no autograd node) is ``thunder_speech_b200.train.CTCTrainStep.step``."""
+        from .train import CTCTrainStep
+
+        step = self.__dict__.get("_b200_step")
+        if step is None:
+            step = self.__dict__["_b200_step"] = CTCTrainStep(self)
+        audio, audio_lengths, texts = batch
+        y, y_lengths = self.text_transform.encode(texts, device=audio.device)
+        return step.autograd_loss(audio, audio_lengths, y, y_lengths)
+
     @torch.no_grad()
     def predict_graphed(self, x: Tensor) -> List[str]:
         _, col, cnt = self.predict_ids_graphed(x)

@@ -752,6 +752,45 @@ class FusedAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
 
 
+class _CTCLossFn(torch.autograd.Function):
+    """Bridge between the kernel-written gradients and torch.autograd (see CTCTrainStep.autograd_loss)."""
+
+    @staticmethod
+    def forward(ctx, step, audio, lengths, y, y_lengths, *params):
+        flat = step.flat
+        fresh = [p.grad is None for p in step.params]
+        ensure_grad_views(step.params, flat)
+        if all(fresh):
+            prev = None                      # nothing accumulated so far: param.grad starts from zero
+        else:
+            for p, f in zip(step.params, fresh):
+                if f:
+                    p.grad.zero_()
+            prev = flat.clone()              # gradients accumulated by earlier backward() calls survive this step
+        loss = step.loss_and_grads(audio, lengths, y, y_lengths)       # the kernels overwrite `flat`
+        ctx.grads = flat.clone()
+        if prev is None:
+            flat.zero_()
+        else:
+            flat.copy_(prev)
+        ctx.step = step
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        step, g = ctx.step, ctx.grads
+        ctx.grads = None
+        if g is None:
+            raise RuntimeError("CTCTrainStep.autograd_loss: backward() called twice on the same loss")
+        g.mul_(gout)
+        out, off = [], 0
+        for p in step.params:
+            n = p.numel()
+            out.append(g[off:off + n].view_as(p) if p.requires_grad else None)
+            off += n
+        return (None, None, None, None, None, *out)
+
+
 class _StepGraph:
     """One captured forward + loss + backward for fixed input shapes."""
 
@@ -844,8 +883,9 @@ class CTCTrainStep:
             loss = self._forward_backward(audio, lengths, y, y_lengths)
             self._bump_buffer_versions()
             return loss
-        if ensure_grad_views(self.params, self.flat):
-            self._graphs.clear()          # the captured graphs wrote into gradient tensors that are no longer attached
+        # user code may have dropped / replaced param.grad (zero_grad(set_to_none=True)); the captured graphs write into the
+        # flat buffer itself, so re-attaching the views is all that is needed
+        ensure_grad_views(self.params, self.flat)
         ptrs = tuple(p.data_ptr() for p in self.params)
         if ptrs != getattr(self, "_captured_ptrs", ptrs):
             self._graphs.clear()          # parameters were re-allocated: the captured graphs point at stale storage
@@ -887,6 +927,14 @@ class CTCTrainStep:
         self.allreduce_grads()
         self.opt.step()
         return loss
+
+    def autograd_loss(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
+        """The loss as a node of torch's autograd graph, for callers that drive the optimisation themselves the way
+        Lightning's automatic optimisation drives the reference (``loss = training_step(...); loss.backward();
+        optimizer.step(); optimizer.zero_grad()``): forward runs the whole captured forward + loss + backward, ``backward()``
+        hands the finished parameter gradients to autograd, which ACCUMULATES them into ``param.grad`` as usual (gradient
+        accumulation over micro-batches and ``zero_grad(set_to_none=True)`` both behave like torch)."""
+        return _CTCLossFn.apply(self, audio, lengths, y, y_lengths, *self.params)
 
     def fit_stream(self, batches, depth: int = 2):
         """Training loop over HOST batches ``(audio, audio_lengths, y, y_lengths)`` of one fixed shape (pinned memory for
