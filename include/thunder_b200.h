@@ -36,6 +36,7 @@ extern "C" {
 #define TS_F32 0
 #define TS_BF16 1
 #define TS_I16 2   /* int16 PCM (ts_pcm_ingest only) */
+#define TS_FIX32 3 /* int64 fixed point in units of 2^-32 (SqueezeExcite pool sums: order-independent integer atomics) */
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* ts_version(void);
@@ -101,18 +102,20 @@ int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float*
  *   w0 [Cout, cin0] bf16, x0 bf16 rows [B, cin0, x0_pitch]; segment 1 likewise or NULL/0
  *   lens [B] i32 or NULL: frames t >= lens[b] are stored as zero (input mask of the next MaskedConv1d)
  *   out  bf16 rows [B, Cout, out_pitch] (pitch % 64 == 0) or f32 [B, Cout, out_pitch]
- * SqueezeExcite (citrinet/blocks.py:70-83): `pool` [B, Cout] f32 accumulates sum_t (acc + shift) over t < T
- * (atomicAdd; caller zeroes it); `se_scale` [B, Cout] + `y1` bf16 rows: out = epi(acc + shift + se_scale * y1). */
+ * SqueezeExcite (citrinet/blocks.py:70-83): `pool` [B, Cout] TS_FIX32 (int64, units of 2^-32; caller zeroes it)
+ * accumulates sum_t (acc + shift) over t < T with INTEGER atomics, so the sums -- and with them the logits -- do not
+ * depend on the order in which the tiles of an utterance finish; `se_scale` [B, Cout] + `y1` bf16 rows:
+ * out = epi(acc + shift + se_scale * y1). */
 int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-               int out_dtype, int out_pitch, int relu, float* pool, const float* se_scale, const void* y1,
+               int out_dtype, int out_pitch, int relu, int64_t* pool, const float* se_scale, const void* y1,
                int y1_pitch, void* stream);
 
 /* ---- (4) SqueezeExcite FC, greedy CTC ------------------------------------------------------- */
 /* gate[b, :] = sigmoid(W2 relu(W1 (pool[b, :] / T)))  -- SqueezeExcite.fc + sigmoid (citrinet/blocks.py:63-83).
- *   pool [B, C] f32 sums over all T frames, w1 [H, C] f32, w2 [C, H] f32 (nn.Linear layouts, no bias),
- *   hid [B, H] f32 scratch (the ReLU'd hidden layer), gate [B, C] f32 out */
-int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* hid,
+ *   pool [B, C] sums over all T frames: TS_FIX32 as ts_pw_gemm accumulates them, or TS_F32; w1 [H, C] f32,
+ *   w2 [C, H] f32 (nn.Linear layouts, no bias), hid [B, H] f32 scratch (the ReLU'd hidden layer), gate [B, C] f32 out */
+int ts_se_fc(const void* pool, int pool_dtype, int B, int C, int H, int T, const float* w1, const float* w2, float* hid,
              float* gate, void* stream);
 
 /* out = relu(gate[b, c] * y1[b, c, t]) over bf16 rows: SqueezeExcite scale + `mout` ReLU for blocks without a

@@ -182,12 +182,31 @@ def test_pw_gemm_squeeze_excite_epilogues():
     x0 = rng.standard_normal((B, C, T)).astype(np.float32)
     shift = rng.standard_normal(C).astype(np.float32)
     # squeeze: pooled sums of (acc + shift) over ALL T frames (citrinet/blocks.py:77, no mask)
-    pool = torch.zeros((B, C), device="cuda")
+    pool = torch.zeros((B, C), device="cuda", dtype=torch.int64)     # fixed-point sums (2^-32 units), integer atomics
     y1 = ops.pw_gemm(dev(w0, torch.bfloat16), to_rows(x0), None, None, T, dev(shift), None, False, False, pool, None,
                      None)
     ref1 = gemm_ref(w0, x0, shift=shift)
-    emax, _ = rel_err(pool.cpu().numpy(), ref1.sum(-1))
+    emax, _ = rel_err(ops.se_pool_to_float(pool).cpu().numpy(), ref1.sum(-1))
     assert emax < 1e-4
+    with pytest.raises(TypeError):
+        ops.pw_gemm(dev(w0, torch.bfloat16), to_rows(x0), None, None, T, dev(shift), None, False, False,
+                    torch.zeros((B, C), device="cuda"), None, None)
+    # order-independent accumulation: a long utterance (many frame tiles per channel) pools to the same bits every time, and
+    # the excitation computed from the fixed-point sums equals the one computed from their float value
+    xl = rng.standard_normal((3, C, 2001)).astype(np.float32)
+    pools = []
+    for _ in range(3):
+        pl = torch.zeros((3, C), device="cuda", dtype=torch.int64)
+        ops.pw_gemm(dev(w0, torch.bfloat16), to_rows(xl), None, None, 2001, dev(shift), None, False, False, pl, None, None)
+        pools.append(pl)
+    assert torch.equal(pools[0], pools[1]) and torch.equal(pools[0], pools[2])
+    emax, _ = rel_err(ops.se_pool_to_float(pools[0]).cpu().numpy(), gemm_ref(w0, xl, shift=shift).sum(-1))
+    assert emax < 1e-4
+    fw1 = dev((rng.standard_normal((32, C)) / 16).astype(np.float32))
+    fw2 = dev((rng.standard_normal((C, 32)) / 6).astype(np.float32))
+    g_fix = ops.se_fc(pools[0], 2001, fw1, fw2)
+    g_f32 = ops.se_fc(ops.se_pool_to_float(pools[0]), 2001, fw1, fw2)
+    assert (g_fix - g_f32).abs().max() < 1e-6
     # excite: out = relu(acc_res + shift_res + gate * y1)
     wr = (rng.standard_normal((C, C)) / 16).astype(np.float32)
     xr = rng.standard_normal((B, C, T)).astype(np.float32)

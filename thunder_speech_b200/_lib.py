@@ -20,6 +20,7 @@ TS_ERR_NO_DEVICE = -3
 TS_F32 = 0
 TS_BF16 = 1
 TS_I16 = 2
+TS_FIX32 = 3
 TS_DW_INPUT_PREMASKED = 1
 
 _lib = None
@@ -41,7 +42,7 @@ SIGNATURES = {
     "ts_pw_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p]),
-    "ts_se_fc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ts_se_fc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_se_apply": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ts_ctc_greedy": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p]),

@@ -59,13 +59,18 @@ __global__ void lengths_i32_to_i64_kernel(const int32_t* __restrict__ in, int64_
 // Two kernels so that both FCs spread over (units / 16) x B CTAs instead of one CTA per utterance:
 //   se_hidden_kernel: hid[b, h] = relu(sum_c W1[h, c] * pool[b, c] / T)      grid (ceil(H/16), B), 8 warps x 2 units
 //   se_gate_kernel:   gate[b, c] = sigmoid(sum_h W2[c, h] * hid[b, h])       grid (ceil(C/64), B), 8 warps x 8 units
+template <bool FIXED>
 __global__ void __launch_bounds__(256)
-se_hidden_kernel(const float* __restrict__ pool, float inv_T, const float* __restrict__ w1, int C, int H,
+se_hidden_kernel(const void* __restrict__ pool_, float inv_T, const float* __restrict__ w1, int C, int H,
                  float* __restrict__ hid) {
   extern __shared__ float sm[];   // mean[C]
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = pool[(size_t)b * C + c] * inv_T;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const size_t i = (size_t)b * C + c;
+    const float v = FIXED ? se_pool_value(static_cast<const long long*>(pool_)[i]) : static_cast<const float*>(pool_)[i];
+    sm[c] = v * inv_T;
+  }
   __syncthreads();
   const int h0 = blockIdx.x * 16 + warp * 2;
   float a0 = 0.f, a1 = 0.f;
@@ -280,14 +285,18 @@ extern "C" int ts_lengths_to_i64(const int32_t* in, int64_t* out, int B, void* s
   return TS_OK;
 }
 
-extern "C" int ts_se_fc(const float* pool, int B, int C, int H, int T, const float* w1, const float* w2, float* hid,
-                        float* gate, void* stream) {
+extern "C" int ts_se_fc(const void* pool, int pool_dtype, int B, int C, int H, int T, const float* w1, const float* w2,
+                        float* hid, float* gate, void* stream) {
+  TS_REQUIRE(pool_dtype == TS_F32 || pool_dtype == TS_FIX32, TS_ERR_INVALID, "ts_se_fc: pool must be TS_F32 or TS_FIX32");
   TS_REQUIRE(pool && w1 && w2 && hid && gate, TS_ERR_INVALID, "ts_se_fc: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && H > 0 && T > 0 && B <= 65535, TS_ERR_INVALID, "ts_se_fc: bad sizes");
   TS_REQUIRE((size_t)C * sizeof(float) <= 48 * 1024 && (size_t)H * sizeof(float) <= 48 * 1024, TS_ERR_UNSUPPORTED,
              "ts_se_fc: C=%d / H=%d too large", C, H);
   dim3 g1(ceil_div(H, 16), B), g2(ceil_div(C, 64), B);
-  misc::se_hidden_kernel<<<g1, 256, C * sizeof(float), (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, C, H, hid);
+  if (pool_dtype == TS_FIX32)
+    misc::se_hidden_kernel<true><<<g1, 256, C * sizeof(float), (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, C, H, hid);
+  else
+    misc::se_hidden_kernel<false><<<g1, 256, C * sizeof(float), (cudaStream_t)stream>>>(pool, 1.0f / (float)T, w1, C, H, hid);
   TS_LAUNCH_CHECK("se_hidden_kernel");
   misc::se_gate_kernel<<<g2, 256, H * sizeof(float), (cudaStream_t)stream>>>(hid, w2, C, H, gate);
   TS_LAUNCH_CHECK("se_gate_kernel");

@@ -47,7 +47,7 @@ struct Params {
   int out_pitch;
   int out_f32;
   int relu;
-  float* pool;                 // SE squeeze: [B, Cout] running sums over t < T of the pre-activation output
+  unsigned long long* pool;    // SE squeeze: [B, Cout] fixed-point (2^-32) sums over t < T of the pre-activation output
   const float* se_scale;       // SE excite:  [B, Cout] sigmoid gate applied to y1 before the residual add
   const __nv_bfloat16* y1;     // main-branch output [B, Cout, y1_pitch] read by the SE-apply epilogue
   int y1_pitch;
@@ -207,7 +207,7 @@ pw_gemm_kernel(const __grid_constant__ Params p) {
       }
       }  // m_ok
     }
-    if (p.pool && m_ok) atomicAdd(p.pool + (size_t)b * p.Cout + m, pooled);
+    if (p.pool && m_ok) se_pool_add(p.pool + (size_t)b * p.Cout + m, pooled);
     ptx::tc_fence_before();
   }
   __syncthreads();
@@ -223,11 +223,11 @@ pw_gemm_kernel(const __grid_constant__ Params p) {
 namespace ts {
 int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                        int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-                       int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                       int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
                        cudaStream_t st);
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-                        int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                        int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
                         cudaStream_t st, float* stats = nullptr);
 int option_pw_pair();
 }
@@ -250,8 +250,9 @@ extern "C" int ts_pw_gemm_stats(const void* w, const void* x, int cin, int x_pit
 // Host side: see include/thunder_b200.h for the contract.
 extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1,
                           int cin1, int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens,
-                          void* out, int out_dtype, int out_pitch, int relu, float* pool, const float* se_scale,
+                          void* out, int out_dtype, int out_pitch, int relu, int64_t* pool_fixed, const float* se_scale,
                           const void* y1, int y1_pitch, void* stream) {
+  unsigned long long* pool = reinterpret_cast<unsigned long long*>(pool_fixed);
   TS_REQUIRE(w0 && x0 && out, TS_ERR_INVALID, "ts_pw_gemm: null pointer");
   TS_REQUIRE(B > 0 && Cout > 0 && T > 0 && cin0 > 0, TS_ERR_INVALID, "ts_pw_gemm: bad sizes");
   TS_REQUIRE(cin0 % 8 == 0 && (cin1 % 8 == 0), TS_ERR_UNSUPPORTED,

@@ -48,7 +48,7 @@ struct Params {
   const int32_t* lens;
   int out_pitch;
   int relu;
-  float* pool;
+  unsigned long long* pool;
   const float* se_scale;
   const __nv_bfloat16* y1;
   int y1_pitch;
@@ -256,7 +256,7 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
           }
         }
       }
-      if (p.pool && m_ok) atomicAdd(p.pool + (size_t)b * p.Cout + m, pooled);
+      if (p.pool && m_ok) se_pool_add(p.pool + (size_t)b * p.Cout + m, pooled);
     }
     if (lane == 0) bulk_wait0();   // all stores of this warp are complete before the CTA exits
   }
@@ -273,7 +273,7 @@ pw_gemm_big_kernel(const __grid_constant__ Params p) {
 // bf16-row outputs with Cout > 128; returns TS_ERR_UNSUPPORTED for anything else (caller falls back to pwgemm.cu)
 int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                        int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-                       int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                       int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
                        cudaStream_t st) {
   if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
   pw2::Params p;

@@ -40,7 +40,7 @@ struct Params {
   float* stats;        // optional [B, Cout, 2 * n_tiles, 2]: (sum, sum of squares) of the STORED bf16 values per 128-frame block
   int out_pitch;
   int relu;
-  float* pool;
+  unsigned long long* pool;
   const float* se_scale;
   const __nv_bfloat16* y1;
   int y1_pitch;
@@ -320,7 +320,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
           }
         }
       }
-      if (p.pool && m_ok) atomicAdd(p.pool + (size_t)b * p.Cout + m, pooled);
+      if (p.pool && m_ok) se_pool_add(p.pool + (size_t)b * p.Cout + m, pooled);
       if (p.stats && m_ok)   // one slot per (row, 128-frame block): written exactly once, no atomics (deterministic)
         *reinterpret_cast<float2*>(p.stats + ((((size_t)b * p.Cout + m) * (2 * p.n_tiles)) + nt * 2 + h) * 2) =
             make_float2(st_s, st_ss);
@@ -340,7 +340,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
 // bf16-row outputs with Cout > 128 on CTA pairs; TS_ERR_UNSUPPORTED otherwise (caller falls back)
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-                        int out_pitch, int relu, float* pool, const float* se_scale, const void* y1, int y1_pitch,
+                        int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
                         cudaStream_t st, float* stats) {
   if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
   pw3::Params p;

@@ -82,6 +82,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // ---- device helpers ---------------------------------------------------------------------------
+// SqueezeExcite time-pooling accumulator: partial sums are added as 64-bit FIXED-POINT integers (units of 2^-32), so the
+// result does not depend on the order in which the tiles of an utterance arrive (fp32 atomics do: last-bit differences of
+// the gate were amplified to O(1) logit differences, run to run, by a 115-layer random-init Citrinet).  |sum| < 2^31.
+constexpr float kSePoolScale = 4294967296.f;   // 2^32
+__device__ __forceinline__ void se_pool_add(unsigned long long* slot, float partial) {
+  atomicAdd(slot, static_cast<unsigned long long>(__float2ll_rn(partial * kSePoolScale)));
+}
+__device__ __forceinline__ float se_pool_value(long long fixed) { return static_cast<float>(static_cast<double>(fixed) * (1.0 / 4294967296.0)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

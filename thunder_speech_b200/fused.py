@@ -164,7 +164,7 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
                 out = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, out_lens, False, True, None, None, None)
         else:
             B = a.shape[0]
-            pool = torch.zeros((B, plan.out_channels), device=a.device, dtype=torch.float32)
+            pool = torch.zeros((B, plan.out_channels), device=a.device, dtype=torch.int64)   # fixed-point sums
             y1 = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, None, False, False, pool, None, None)
             gate = ops.se_fc(pool, Ta, plan.se_w1, plan.se_w2)
             if xr is not None:

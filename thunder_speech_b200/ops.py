@@ -184,8 +184,12 @@ def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], 
             lens: Optional[Tensor], out_f32: bool, relu: bool, pool: Optional[Tensor], se_scale: Optional[Tensor],
             y1: Optional[Tensor]) -> Tensor:
     """tcgen05 pointwise GEMM with fused BN-shift / residual segment / ReLU / tail mask / SE epilogues.
-    ``w*`` bf16 ``[Cout, Cin]`` (BN scale folded in), ``x*`` bf16 rows ``[B, Cin, pitch]``."""
+    ``w*`` bf16 ``[Cout, Cin]`` (BN scale folded in), ``x*`` bf16 rows ``[B, Cin, pitch]``.  ``pool`` (SqueezeExcite
+    squeeze) is a zeroed int64 ``[B, Cout]``: fixed-point sums in units of 2^-32 (``se_pool_to_float``), accumulated with
+    integer atomics so that the result does not depend on tile order."""
     _need_cuda(w0, x0)
+    if pool is not None and (pool.dtype != torch.int64 or tuple(pool.shape) != (x0.shape[0], w0.shape[0])):
+        raise TypeError("pw_gemm: pool must be an int64 [B, Cout] tensor (fixed-point sums, see se_pool_to_float)")
     B, cin0, p0 = x0.shape
     Cout = w0.shape[0]
     if out_f32:
@@ -220,19 +224,28 @@ def _(w0, x0, w1, x1, T, shift, lens, out_f32, relu, pool, se_scale, y1):
 # ------------------------------------------------------------------------------------------- SE / CTC
 @torch.library.custom_op(f"{NS}::se_fc", mutates_args=())
 def se_fc(pool: Tensor, T: int, w1: Tensor, w2: Tensor) -> Tensor:
-    """``sigmoid(W2 relu(W1 pool/T))`` -> gate ``[B, C]`` f32 (citrinet/blocks.py:63-83)."""
+    """``sigmoid(W2 relu(W1 pool/T))`` -> gate ``[B, C]`` f32 (citrinet/blocks.py:63-83).  ``pool`` holds the sums over all T
+    frames: int64 fixed point as ``pw_gemm`` accumulates them, or plain float32."""
     _need_cuda(pool, w1, w2)
+    if pool.dtype not in (torch.int64, torch.float32):
+        raise TypeError("se_fc: pool must be int64 (fixed point) or float32")
     B, C = pool.shape
-    gate = torch.empty_like(pool)
+    gate = torch.empty((B, C), device=pool.device, dtype=torch.float32)
     hid = torch.empty((B, w1.shape[0]), device=pool.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_se_fc(_ptr(pool), B, C, w1.shape[0], T, _ptr(w1), _ptr(w2), _ptr(hid), _ptr(gate),
+    dt = _lib.TS_FIX32 if pool.dtype == torch.int64 else _lib.TS_F32
+    _lib.check(_lib.lib().ts_se_fc(_ptr(pool), dt, B, C, w1.shape[0], T, _ptr(w1), _ptr(w2), _ptr(hid), _ptr(gate),
                                    _stream()), "ts_se_fc")
     return gate
 
 
 @se_fc.register_fake
 def _(pool, T, w1, w2):
-    return torch.empty_like(pool)
+    return pool.new_empty(pool.shape, dtype=torch.float32)
+
+
+def se_pool_to_float(pool: Tensor) -> Tensor:
+    """The fixed-point SqueezeExcite sums of ``pw_gemm`` (int64, units of 2^-32) as float32."""
+    return (pool.double() * 2.0 ** -32).float()
 
 
 @torch.library.custom_op(f"{NS}::ctc_greedy", mutates_args=())
