@@ -725,6 +725,38 @@ def test_training_step_is_an_autograd_node_like_the_reference():
     assert torch.isfinite(l3) and float(l3.detach()) != float(want_loss)
 
 
+def test_config5_full_size_training_step_properties():
+    """BASELINE config 5 at its full size (QuartzNet 15x5, 32 x 15 s per GPU, ragged lengths, 120-character labels): the
+    captured-graph step and the eager step of an identical model give the same loss and bit-identical gradients (894 kernel
+    launches, forked weight-gradient stream, split-K reductions: no order dependence anywhere), the optimiser moves every
+    parameter, and repeated steps on the batch bring the loss down."""
+    from thunder_speech_b200.runner import build_model
+
+    B, N, L = 32, 15 * 16000, 120
+    rng = np.random.default_rng(5)
+    audio = torch.from_numpy(synth.audio(B, N, 91, "noise")).cuda()
+    lens = torch.from_numpy(synth.ragged_lengths(B, N, 7)).cuda()
+    y = torch.from_numpy(rng.integers(0, 28, (B, L)).astype(np.int64)).cuda()
+    yl = torch.from_numpy(rng.integers(L // 2, L + 1, B).astype(np.int64)).cuda()
+    steps = []
+    for use_graph in (True, False):
+        m = build_model("quartznet15x5", torch.device("cuda"), seed=0)
+        m.encoder.train(); m.decoder.train()             # front-end stays in eval(): no dither noise in this comparison
+        steps.append((m, CTCTrainStep(m, lr=3e-4, use_graph=use_graph)))
+    (m1, s1), (m2, s2) = steps
+    l1 = s1.loss_and_grads(audio, lens, y, yl).clone()
+    l2 = s2.loss_and_grads(audio, lens, y, yl).clone()
+    assert torch.isfinite(l1) and torch.equal(l1, l2)
+    assert torch.equal(s1.flat, s2.flat) and torch.isfinite(s1.flat).all() and float(s1.flat.norm()) > 0
+    for (k, a), (_, b) in zip(m1.named_buffers(), m2.named_buffers()):
+        assert torch.equal(a, b), k                     # BatchNorm running statistics / num_batches_tracked
+    before = [p.detach().clone() for p in s1.params]
+    s1.opt.step()
+    assert all(not torch.equal(a, p) for a, p in zip(before, s1.params))
+    losses = [float(l1)] + [float(s1.step(audio, lens, y, yl)) for _ in range(12)]
+    assert all(np.isfinite(losses)) and min(losses[6:]) < losses[0], losses
+
+
 def test_fit_stream_equals_step_by_step():
     """CTCTrainStep.fit_stream (pinned host batches, copies on a side stream, loss read back one step late) produces the
     same losses and the same weights as calling step() on device tensors, for pipeline depths 1-3."""
