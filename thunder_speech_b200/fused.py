@@ -190,8 +190,9 @@ class PlannedBlock(nn.Module):
     def _check_eval(self):
         if self.training:
             raise NotImplementedError(
-                "thunder_speech_b200 implements the inference (eval) forward path; call .eval() first. "
-                "The training step (batch-statistics BatchNorm, backward kernels) is a later row of SURVEY.md 8(f).")
+                "this entry point is the inference (eval) forward; call .eval() first.  The train()-mode forward with "
+                "batch-statistics BatchNorm and the backward kernels run through CTCModule.training_step / "
+                "thunder_speech_b200.train.CTCTrainStep (whole model) or train.BlockTrainer (one block).")
 
     def forward_rows(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool):
         self._check_eval()

@@ -61,7 +61,8 @@ class CTCModule(nn.Module):
     def forward(self, x: Tensor, lengths: Tensor) -> Tuple[Tensor, Optional[Tensor]]:
         """``(audio[B,N], lengths[B]) -> (logits[B,V,T'] f32, out_lengths[B] i64)`` (module.py:74-86)."""
         if self.training:
-            raise NotImplementedError("inference path only: call .eval() (training step is SURVEY.md 8(f) row 1)")
+            raise NotImplementedError("forward() is the inference path: call .eval(), or use training_step() / "
+                                      "thunder_speech_b200.train.CTCTrainStep for the train()-mode step")
         with torch.no_grad():
             logits, T, l32, _ = self._logits_rows(x, lengths)
             return logits, l32.to(torch.int64)
