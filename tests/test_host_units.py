@@ -318,3 +318,39 @@ def test_product_code_never_touches_the_oracle_or_the_reference():
     end = bench.index("\ndef ", start + 1)
     assert all(start < h < end for h in hits), "oracle imported outside bench.py cpu_port_rate()"
     assert "/root/reference" not in bench
+
+
+def test_error_rate_metrics_match_levenshtein_definition():
+    """thunder_speech_b200.metrics (stand-in for torchmetrics' CharErrorRate / WordErrorRate used by validation_step,
+    src/thunder/module.py:17-18,157-162): vectorised edit distance == the textbook DP; rates accumulate as
+    total errors / total target length."""
+    import random
+
+    from thunder_speech_b200.metrics import CharErrorRate, WordErrorRate, edit_distance
+
+    def dp(a, b):
+        d = list(range(len(b) + 1))
+        for i, x in enumerate(a, 1):
+            nd = [i]
+            for j, yv in enumerate(b, 1):
+                nd.append(min(d[j] + 1, nd[j - 1] + 1, d[j - 1] + (x != yv)))
+            d = nd
+        return d[-1]
+
+    rnd = random.Random(0)
+    for _ in range(500):
+        a = "".join(rnd.choice("abc ") for _ in range(rnd.randint(0, 14)))
+        b = "".join(rnd.choice("abc ") for _ in range(rnd.randint(0, 14)))
+        assert edit_distance(a, b) == dp(a, b)
+        assert edit_distance(a.split(), b.split()) == dp(a.split(), b.split())
+    cer, wer = CharErrorRate(), WordErrorRate()
+    assert cer(["abc", "hello"], ["abd", "hallo"]) == pytest.approx(2 / 8)
+    assert cer("", "ab") == pytest.approx(1.0)
+    assert cer.compute() == pytest.approx(4 / 10)
+    assert wer(["the cat sat"], ["the cat sat down"]) == pytest.approx(0.25)
+    assert wer(["a b c d"], ["a x c"]) == pytest.approx(2 / 3)
+    assert wer.compute() == pytest.approx(3 / 7)
+    wer.reset()
+    assert np.isnan(wer.compute())
+    with pytest.raises(ValueError):
+        cer(["a"], ["a", "b"])

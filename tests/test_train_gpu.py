@@ -757,6 +757,32 @@ def test_config5_full_size_training_step_properties():
     assert all(np.isfinite(losses)) and min(losses[6:]) < losses[0], losses
 
 
+def test_validation_step_loss_and_error_rates():
+    """CTCModule.validation_step (module.py:130-163): eval() forward, CTC loss == F.ctc_loss(log_softmax(logits)) with the
+    encoder's output lengths (reduction mean, zero_infinity), predictions decoded from every frame, CER / WER accumulated
+    against the label strings."""
+    from thunder_speech_b200.metrics import CharErrorRate, WordErrorRate
+
+    case = _model_case()
+    m, _, batch = _device_model(case)
+    texts = ["hello world", "a test", "speech", "b two hundred", "x", "quartz net", "ctc", "gpu"]
+    with pytest.raises(NotImplementedError):
+        m.validation_step((batch[0], batch[1], texts), 0)          # still in train() mode
+    m.eval()
+    loss = m.validation_step((batch[0], batch[1], texts), 0)
+    logits, out_len = m(batch[0], batch[1])
+    y, yl = m.text_transform.encode(texts, device="cuda")
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(logits.double(), 1).permute(2, 0, 1), y, out_len, yl,
+                                       blank=m.text_transform.vocab.blank_idx, reduction="mean", zero_infinity=True)
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)), (float(loss), float(ref))
+    preds = m.text_transform.decode_prediction(logits.argmax(1))    # the reference's formula on the same logits
+    cer, wer = CharErrorRate(), WordErrorRate()
+    cer(preds, texts); wer(preds, texts)
+    assert m.validation_cer.compute() == cer.compute() and m.validation_wer.compute() == wer.compute()
+    m.validation_step((batch[0], batch[1], texts), 1)              # accumulates over batches
+    assert m.validation_cer.total == 2 * cer.total and m.validation_cer.compute() == cer.compute()
+
+
 def test_fit_stream_equals_step_by_step():
     """CTCTrainStep.fit_stream (pinned host batches, copies on a side stream, loss read back one step late) produces the
     same losses and the same weights as calling step() on device tensors, for pipeline depths 1-3."""

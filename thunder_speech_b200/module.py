@@ -30,6 +30,11 @@ class CTCModule(nn.Module):
         self.decoder = decoder
         self.text_transform = text_transform
         self.encoder_final_dimension = encoder_final_dimension
+        # metrics of validation_step (module.py:67-68 keeps torchmetrics' CharErrorRate / WordErrorRate)
+        from .metrics import CharErrorRate, WordErrorRate
+
+        self.validation_cer = CharErrorRate()
+        self.validation_wer = WordErrorRate()
         self._dec_cache = None
         self._graphs: Dict[Tuple[int, int], "_PredictGraph"] = {}
         self._pipes: Dict[tuple, "_StreamPipe"] = {}
@@ -106,6 +111,27 @@ class CTCModule(nn.Module):
         audio, audio_lengths, texts = batch
         y, y_lengths = self.text_transform.encode(texts, device=audio.device)
         return step.autograd_loss(audio, audio_lengths, y, y_lengths)
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx: int = 0) -> Tensor:
+        """``BaseCTCModule.validation_step`` (src/thunder/module.py:130-163), eval() mode: ``batch = (audio, audio_lengths,
+        texts)`` -> mean CTC loss (the CTC kernel on the fp32 logits with the encoder's output lengths, like
+        ``calculate_ctc``); greedy transcriptions of EVERY frame (``probabilities.argmax(1)``) and the label strings update
+        ``validation_cer`` / ``validation_wer``."""
+        from .train import ctc_loss
+
+        audio, audio_lengths, texts = batch
+        y, y_lengths = self.text_transform.encode(texts, device=audio.device)
+        if self.training:
+            raise NotImplementedError("validation_step() runs the eval() forward (Lightning switches to eval for validation)")
+        logits, T, l32, _ = self._logits_rows(audio, audio_lengths)
+        loss_b, _ = ctc_loss(logits, T, l32, y, y_lengths.to(torch.int64), self.text_transform.vocab.blank_idx)
+        _, col, cnt = ops.ctc_greedy(logits, T, -1)
+        decoded_preds = self.text_transform.decode_collapsed(col, cnt)
+        decoded_targets = self.text_transform.decode_prediction(y, remove_repeated=False)
+        self.validation_cer(decoded_preds, decoded_targets)
+        self.validation_wer(decoded_preds, decoded_targets)
+        return loss_b.mean()
 
     @torch.no_grad()
     def predict_graphed(self, x: Tensor) -> List[str]:
