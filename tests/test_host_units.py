@@ -354,3 +354,30 @@ def test_error_rate_metrics_match_levenshtein_definition():
     assert np.isnan(wer.compute())
     with pytest.raises(ValueError):
         cer(["a"], ["a", "b"])
+
+
+def test_ctc_module_constructor_and_configure_optimizers_like_the_reference():
+    """BaseCTCModule's constructor arguments and configure_optimizers (src/thunder/module.py:26-64,165-192)."""
+    import types
+
+    from thunder_speech_b200.module import BaseCTCModule
+
+    def make(**kw):
+        enc = QuartznetEncoder(filters=[16, 16, 16, 16, 16], kernel_sizes=[3, 3, 3, 3, 3], repeat_blocks=1)
+        return BaseCTCModule(enc, conv1d_decoder(1024, 29), FilterbankFeatures(), BatchTextTransformer(synth.quartznet_vocab()), **kw)
+
+    m = make()
+    opt = m.configure_optimizers()
+    assert isinstance(opt, torch.optim.AdamW)
+    assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == sum(p.numel() for p in m.parameters())
+    m = make(optimizer_class=torch.optim.SGD, optimizer_kwargs={"lr": 0.1, "momentum": 0.9},
+             lr_scheduler_class=torch.optim.lr_scheduler.OneCycleLR,
+             lr_scheduler_kwargs={"max_lr": 0.5, "total_steps_arg": "total_steps", "interval": "epoch"},
+             encoder_final_dimension=1024)
+    with pytest.raises(RuntimeError):
+        m.configure_optimizers()                      # total_steps_arg needs the trainer
+    m.trainer = types.SimpleNamespace(estimated_stepping_batches=123)
+    cfg = m.configure_optimizers()
+    assert isinstance(cfg["optimizer"], torch.optim.SGD) and cfg["optimizer"].defaults["momentum"] == 0.9
+    assert cfg["lr_scheduler"]["interval"] == "epoch" and cfg["lr_scheduler"]["scheduler"].total_steps == 123
+    assert m.encoder_final_dimension == 1024 and "total_steps_arg" in m.lr_scheduler_kwargs   # kwargs left intact

@@ -23,12 +23,20 @@ __all__ = ["CTCModule", "BaseCTCModule"]
 
 class CTCModule(nn.Module):
     def __init__(self, encoder: nn.Module, decoder: nn.Module, audio_transform: nn.Module,
-                 text_transform: nn.Module, encoder_final_dimension: Optional[int] = None):
+                 text_transform: nn.Module, optimizer_class=torch.optim.AdamW, optimizer_kwargs: Optional[Dict] = None,
+                 lr_scheduler_class=None, lr_scheduler_kwargs: Optional[Dict] = None,
+                 encoder_final_dimension: Optional[int] = None):
+        """Same constructor as ``BaseCTCModule`` (src/thunder/module.py:26-64), argument for argument."""
         super().__init__()
         self.audio_transform = audio_transform
         self.encoder = encoder
         self.decoder = decoder
         self.text_transform = text_transform
+        self.optimizer_class = optimizer_class
+        self.optimizer_kwargs = dict(optimizer_kwargs or {})
+        self.lr_scheduler_class = lr_scheduler_class
+        self.lr_scheduler_kwargs = dict(lr_scheduler_kwargs or {})
+        self.lr_scheduler_interval = self.lr_scheduler_kwargs.pop("interval", "step")
         self.encoder_final_dimension = encoder_final_dimension
         # metrics of validation_step (module.py:67-68 keeps torchmetrics' CharErrorRate / WordErrorRate)
         from .metrics import CharErrorRate, WordErrorRate
@@ -111,6 +119,28 @@ class CTCModule(nn.Module):
         audio, audio_lengths, texts = batch
         y, y_lengths = self.text_transform.encode(texts, device=audio.device)
         return step.autograd_loss(audio, audio_lengths, y, y_lengths)
+
+    def _update_special_optimizer_arg(self, original_kwargs: Dict) -> Dict:
+        """``total_steps_arg="<name>"`` is replaced by ``<name>=trainer.estimated_stepping_batches`` (module.py:165-171)."""
+        updated = dict(original_kwargs)
+        total_steps_arg = updated.pop("total_steps_arg", None)
+        if total_steps_arg:
+            trainer = getattr(self, "trainer", None)
+            if trainer is None:
+                raise RuntimeError("total_steps_arg needs a Lightning trainer attached to the module (self.trainer)")
+            updated[total_steps_arg] = trainer.estimated_stepping_batches
+        return updated
+
+    def configure_optimizers(self):
+        """``BaseCTCModule.configure_optimizers`` (module.py:173-192): ``optimizer_class`` over the trainable parameters,
+        optionally with ``lr_scheduler_class`` in Lightning's dictionary form.  The optimizer consumes ``param.grad`` as
+        delivered by ``training_step(...).backward()``."""
+        optimizer = self.optimizer_class(filter(lambda p: p.requires_grad, self.parameters()),
+                                         **self._update_special_optimizer_arg(self.optimizer_kwargs))
+        if not self.lr_scheduler_class:
+            return optimizer
+        scheduler = self.lr_scheduler_class(optimizer, **self._update_special_optimizer_arg(self.lr_scheduler_kwargs))
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler, "interval": self.lr_scheduler_interval}}
 
     @torch.no_grad()
     def validation_step(self, batch, batch_idx: int = 0) -> Tensor:
