@@ -801,13 +801,13 @@ class _StepGraph:
 
 
 class CTCTrainStep:
-    """One optimisation step of a ``CTCModule`` (QuartzNet family), mirroring ``BaseCTCModule.training_step`` +
-    ``configure_optimizers`` (src/thunder/module.py:102-127, :129-140): features (no grad) -> encoder forward (kernels) ->
+    """One optimisation step of a ``CTCModule`` (QuartzNet and Citrinet encoders), mirroring ``BaseCTCModule.training_step`` +
+    ``configure_optimizers`` (src/thunder/module.py:102-127, :173-192): features (no grad) -> encoder forward (kernels) ->
     decoder GEMM -> CTC loss kernel -> decoder / encoder backward (kernels) -> gradient all-reduce (NCCL when initialised)
-    -> AdamW (torch's fused multi-tensor kernel, as the reference uses torch.optim.AdamW).
+    -> AdamW (``FusedAdamW``: torch.optim.AdamW's update rule -- the reference's default optimizer -- in one kernel launch).
 
     All gradients live in ONE flat fp32 buffer (``param.grad`` are views): the all-reduce is a single in-place collective.
-    With ``use_graph`` the whole forward + loss + backward (~1400 launches for QuartzNet 15x5) is captured in a CUDA graph
+    With ``use_graph`` the whole forward + loss + backward (~890 launches for QuartzNet 15x5) is captured in a CUDA graph
     per input shape and replayed; inputs are copied into the graph's static buffers."""
 
     def __init__(self, module, lr: float = 3e-4, blank_idx: Optional[int] = None,
