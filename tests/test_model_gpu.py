@@ -131,6 +131,16 @@ def test_predict_matches_oracle_decode(golden_e2e, model):
     assert torch.equal(ids2, ids) and torch.equal(col2, col) and torch.equal(cnt2, cnt)
     ids3, _, _ = m.predict_ids_graphed(xd)
     assert torch.equal(ids3, ids)
+    # in-place graph: reads the caller's persistent buffer where it lies (no staging copy), sees new contents on replay
+    buf = xd.clone()
+    ids4, col4, _ = m.predict_ids_graphed(buf, in_place=True)
+    assert torch.equal(ids4, ids) and torch.equal(col4, col)
+    x2 = torch.from_numpy(synth.audio(2, 12000, 22, "tones")).cuda()
+    want2, _, _ = m.predict_ids(x2)
+    buf.copy_(x2)
+    ids5, _, _ = m.predict_ids_graphed(buf, in_place=True)
+    assert torch.equal(ids5, want2) and not torch.equal(want2, ids)
+    assert len([k for k in m._graphs if k[2] is not None]) == 1
 
 
 def test_batch_independence():

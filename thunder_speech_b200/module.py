@@ -6,8 +6,9 @@
 
 ``forward`` keeps activations in the kernels' bf16 row layout from the feature kernel to the decoder GEMM and
 returns fp32 logits ``[B, V, T']`` like the reference.  ``predict`` adds the greedy CTC kernel and detokenises
-on the host after a single device-to-host copy.  Optimiser / metric / training-step plumbing of the reference
-class (module.py:102-189) is Lightning glue outside the forward hot path.
+on the host after a single device-to-host copy.  ``training_step`` / ``validation_step`` / ``configure_optimizers``
+(module.py:102-192) keep the reference's signatures on top of ``thunder_speech_b200.train`` (kernel backward behind one
+autograd node); Lightning itself (logging, trainer hooks) is not part of this package.
 """
 from __future__ import annotations
 
@@ -44,7 +45,7 @@ class CTCModule(nn.Module):
         self.validation_cer = CharErrorRate()
         self.validation_wer = WordErrorRate()
         self._dec_cache = None
-        self._graphs: Dict[Tuple[int, int], "_PredictGraph"] = {}
+        self._graphs: Dict[tuple, "_PredictGraph"] = {}
         self._pipes: Dict[tuple, "_StreamPipe"] = {}
 
     # -- decoder parameters as GEMM operands ----------------------------------------------------
@@ -95,13 +96,15 @@ class CTCModule(nn.Module):
 
     # -- CUDA-graph replay of predict_ids for a fixed (batch, samples) shape -----------------------
     @torch.no_grad()
-    def predict_ids_graphed(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    def predict_ids_graphed(self, x: Tensor, in_place: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
         """Same result as :meth:`predict_ids`; the ~200 kernel launches of one forward are captured once per
-        input shape into a CUDA graph and replayed (launch-bound otherwise at small batch)."""
-        key = (x.shape[0], x.shape[1])
+        input shape into a CUDA graph and replayed (launch-bound otherwise at small batch).  By default the audio is
+        copied into the graph's own input buffer; ``in_place=True`` declares ``x`` a persistent device buffer owned by the
+        caller (a DMA staging buffer): the graph captured for it reads ``x`` where it lies, one graph per such buffer."""
+        key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None)
         g = self._graphs.get(key)
         if g is None:
-            g = _PredictGraph(self, x)
+            g = _PredictGraph(self, x, in_place)
             self._graphs[key] = g
         return g.replay(x)
 
@@ -230,7 +233,8 @@ class _StreamPipe:
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
         self.stage_free = [torch.cuda.Event() for _ in range(depth)]
         self.d2h_done = [torch.cuda.Event() for _ in range(depth)]
-        _, col, cnt = module.predict_ids_graphed(self.stage[0])   # builds / warms the graph for this shape
+        for st in self.stage:                                     # one in-place graph per staging buffer (no D2D copy)
+            _, col, cnt = module.predict_ids_graphed(st, in_place=True)
         torch.cuda.synchronize(dev)
         self.host_col = [torch.empty(col.shape, dtype=col.dtype).pin_memory() for _ in range(depth)]
         self.host_cnt = [torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory() for _ in range(depth)]
@@ -249,7 +253,7 @@ class _StreamPipe:
             self.stage[s].copy_(xb, non_blocking=True)
             self.h2d_done[s].record(self.copy_stream)
         cur.wait_event(self.h2d_done[s])
-        _, col, cnt = self.m.predict_ids_graphed(self.stage[s])
+        _, col, cnt = self.m.predict_ids_graphed(self.stage[s], in_place=True)
         self.stage_free[s].record(cur)
         self.host_col[s].copy_(col, non_blocking=True)
         self.host_cnt[s].copy_(cnt, non_blocking=True)
@@ -262,10 +266,10 @@ class _StreamPipe:
 
 
 class _PredictGraph:
-    def __init__(self, module: CTCModule, example: Tensor):
+    def __init__(self, module: CTCModule, example: Tensor, in_place: bool = False):
         from . import _lib
 
-        self.static_in = example.clone()
+        self.static_in = example if in_place else example.clone()
         # warm-up on a side stream (sets kernel attributes, builds plans), then capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -282,7 +286,8 @@ class _PredictGraph:
         self.replays = 0
 
     def replay(self, x: Tensor):
-        self.static_in.copy_(x, non_blocking=True)
+        if x.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         self.replays += 1
         return self.static_out
