@@ -141,6 +141,11 @@ def test_predict_matches_oracle_decode(golden_e2e, model):
     ids5, _, _ = m.predict_ids_graphed(buf, in_place=True)
     assert torch.equal(ids5, want2) and not torch.equal(want2, ids)
     assert len([k for k in m._graphs if k[2] is not None]) == 1
+    keep = [torch.empty_like(buf) for _ in range(m.MAX_IN_PLACE_GRAPHS + 2)]      # many caller buffers: oldest graphs evicted
+    for t in keep:
+        t.copy_(x2)
+        assert torch.equal(m.predict_ids_graphed(t, in_place=True)[0], want2)
+    assert len([k for k in m._graphs if k[2] is not None]) == m.MAX_IN_PLACE_GRAPHS
 
 
 def test_batch_independence():
@@ -190,7 +195,7 @@ def test_full_size_configs_batch_independence_and_masking(name, B, secs):
     assert torch.isfinite(full).all()
 
 
-@pytest.mark.parametrize("depth,nbatch", [(2, 5), (3, 7), (3, 2), (4, 1)])
+@pytest.mark.parametrize("depth,nbatch", [(2, 5), (3, 7), (3, 2), (4, 1), (7, 9)])
 def test_predict_stream_matches_predict(depth, nbatch):
     """The pipelined serving loop (H2D / compute / D2H overlapped, `depth` batches in flight, also fewer batches than
     the pipeline is deep) returns the same strings as predict(), in order."""

@@ -23,6 +23,8 @@ __all__ = ["CTCModule", "BaseCTCModule"]
 
 
 class CTCModule(nn.Module):
+    MAX_IN_PLACE_GRAPHS = 8     # captured graphs kept for caller-owned input buffers (oldest evicted first)
+
     def __init__(self, encoder: nn.Module, decoder: nn.Module, audio_transform: nn.Module,
                  text_transform: nn.Module, optimizer_class=torch.optim.AdamW, optimizer_kwargs: Optional[Dict] = None,
                  lr_scheduler_class=None, lr_scheduler_kwargs: Optional[Dict] = None,
@@ -104,6 +106,10 @@ class CTCModule(nn.Module):
         key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None)
         g = self._graphs.get(key)
         if g is None:
+            if in_place:    # a caller that passes a fresh tensor every time must not accumulate graphs (and their memory pools)
+                stale = [k for k in self._graphs if k[2] is not None]
+                for k in stale[:max(0, len(stale) - (self.MAX_IN_PLACE_GRAPHS - 1))]:
+                    del self._graphs[k]
             g = _PredictGraph(self, x, in_place)
             self._graphs[key] = g
         return g.replay(x)
@@ -233,8 +239,10 @@ class _StreamPipe:
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
         self.stage_free = [torch.cuda.Event() for _ in range(depth)]
         self.d2h_done = [torch.cuda.Event() for _ in range(depth)]
-        for st in self.stage:                                     # one in-place graph per staging buffer (no D2D copy)
-            _, col, cnt = module.predict_ids_graphed(st, in_place=True)
+        # one in-place graph per staging buffer (no D2D copy) while that fits the module's graph budget
+        self.in_place = depth <= module.MAX_IN_PLACE_GRAPHS - 2
+        for st in self.stage:
+            _, col, cnt = module.predict_ids_graphed(st, in_place=self.in_place)
         torch.cuda.synchronize(dev)
         self.host_col = [torch.empty(col.shape, dtype=col.dtype).pin_memory() for _ in range(depth)]
         self.host_cnt = [torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory() for _ in range(depth)]
@@ -253,7 +261,7 @@ class _StreamPipe:
             self.stage[s].copy_(xb, non_blocking=True)
             self.h2d_done[s].record(self.copy_stream)
         cur.wait_event(self.h2d_done[s])
-        _, col, cnt = self.m.predict_ids_graphed(self.stage[s], in_place=True)
+        _, col, cnt = self.m.predict_ids_graphed(self.stage[s], in_place=self.in_place)
         self.stage_free[s].record(cur)
         self.host_col[s].copy_(col, non_blocking=True)
         self.host_cnt[s].copy_(cnt, non_blocking=True)
