@@ -37,6 +37,10 @@ extern "C" {
 #define TS_BF16 1
 #define TS_I16 2   /* int16 PCM (ts_pcm_ingest only) */
 #define TS_FIX32 3 /* int64 fixed point in units of 2^-32 (SqueezeExcite pool sums: order-independent integer atomics) */
+#define TS_F16 4   /* IEEE fp16 activation rows / GEMM operands ("half rows"): same bytes and tensor-core rate as bf16,
+                    * 11-bit mantissa; conversions saturate to +-65504.  Inference entry points only. */
+/* flag shared by the row-consuming inference entry points: the 16-bit rows (and 16-bit weights) are TS_F16, not TS_BF16 */
+#define TS_ROWS_F16 2
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* ts_version(void);
@@ -46,7 +50,8 @@ int64_t ts_launch_count(void);
 /* runtime switches for A/B measurements: "dw_mma" (default 1) = stride-1 depthwise convs on the tensor cores,
  * "pw_big" (default 1) = persistent 256x256-tile GEMM for bf16 outputs with Cout > 128, "pw_pair" (default 2) = run it
  * on CTA pairs (tcgen05 cta_group::2; 1 = only for K >= 1024, 0 = single-CTA kernel),
- * "pdl" (default 0) = programmatic dependent launch for the two hot kernels (measured: no gain),
+ * "pdl" (default 3: bit 0 = depthwise, bit 1 = GEMM) = programmatic dependent launch for the two hot kernels
+ * (measured: +1.7 % on the QuartzNet forward, +6 % on the training step),
  * "dw_tma" (default 1) = TMA-fed Toeplitz kernel for pre-masked inputs, "dw_base_offset" (descriptor experiment) */
 int ts_set_option(const char* name, int value);
 /* pitch (in frames) of a padded activation row holding T frames */
@@ -75,7 +80,7 @@ int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemp
  * (transform.py:77-92 -> src/thunder/blocks.py:118-149): seq_len = floor(len/hop)+1; per (b, feature)
  * masked mean / biased std over t < seq_len, (x-mean)/(std+div_guard), zero for t >= seq_len.
  *   lengths [B] i64 (audio samples)    seq_len_out [B] i64 (may be NULL)
- *   out: f32 -> [B, nfilt, F] (out_pitch == F) or bf16 -> [B, nfilt, out_pitch] padded rows */
+ *   out: f32 -> [B, nfilt, F] (out_pitch == F) or bf16 / fp16 -> [B, nfilt, out_pitch] padded rows */
 int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int nfilt, int F, int hop,
                          float div_guard, void* out, int out_dtype, int out_pitch,
                          int64_t* seq_len_out, void* stream);
@@ -88,7 +93,8 @@ int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int
  *   y  bf16 rows [B, C, pitch_out], T_out = floor((T_in + 2P - D(K-1) - 1)/S) + 1
  * TS_ERR_INVALID when both S > 1 and D > 1 (get_same_padding raises ValueError, src/thunder/blocks.py:192-193).
  *   flags: TS_DW_INPUT_PREMASKED = the caller guarantees x is already zero for t >= len_in[b] (true for rows
- *          produced by ts_pack_rows / ts_pw_gemm / ts_feature_normalize with lengths): enables the TMA-fed kernel */
+ *          produced by ts_pack_rows / ts_pw_gemm / ts_feature_normalize with lengths): enables the TMA-fed kernel;
+ *          TS_ROWS_F16 = x and y are fp16 rows (the Toeplitz taps are then rounded to fp16 as well) */
 #define TS_DW_INPUT_PREMASKED 1
 int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float* w, int K, int S, int D, int P,
                const int32_t* len_in, int flags, void* y, int pitch_out, void* stream);
@@ -106,9 +112,12 @@ int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float*
  * accumulates sum_t (acc + shift) over t < T with INTEGER atomics, so the sums -- and with them the logits -- do not
  * depend on the order in which the tiles of an utterance finish; `se_scale` [B, Cout] + `y1` bf16 rows:
  * out = epi(acc + shift + se_scale * y1). */
+#define TS_PW_RELU 1
+/* flags: TS_PW_RELU = ReLU in the epilogue; TS_ROWS_F16 = w*, x*, y1 (and a 16-bit `out`, out_dtype = TS_F16) are IEEE
+ * fp16 instead of bf16 (same kernels: the tcgen05 kind::f16 instruction descriptor selects the operand format). */
 int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
-               int out_dtype, int out_pitch, int relu, int64_t* pool, const float* se_scale, const void* y1,
+               int out_dtype, int out_pitch, int flags, int64_t* pool, const float* se_scale, const void* y1,
                int y1_pitch, void* stream);
 
 /* ---- (4) SqueezeExcite FC, greedy CTC ------------------------------------------------------- */
@@ -120,7 +129,8 @@ int ts_se_fc(const void* pool, int pool_dtype, int B, int C, int H, int T, const
 
 /* out = relu(gate[b, c] * y1[b, c, t]) over bf16 rows: SqueezeExcite scale + `mout` ReLU for blocks without a
  * residual branch (citrinet/blocks.py:154,195-197); frames t >= lens[b] are stored as zero when lens != NULL */
-int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int relu,
+/* flags: TS_PW_RELU, TS_ROWS_F16 (rows are fp16) */
+int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int flags,
                 void* out, void* stream);
 
 /* Greedy CTC: `pred.argmax(1)` (src/thunder/module.py:100; first maximal index, NaN maximal) followed by the
@@ -138,11 +148,12 @@ int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_in, int S, c
                    int pitch_out, void* stream);
 
 /* ---- layout / length plumbing at module boundaries ------------------------------------------ */
-/* contiguous [B, C, T] (TS_F32 or TS_BF16) -> bf16 rows [B, C, pitch] (frames >= min(T, lens[b]) zero; lens may
- * be NULL) -- the MaskedConv1d.mask_fill of the first consumer (quartznet/blocks.py:158-167) -- and back to f32 */
-int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, const int32_t* lens, void* out, int pitch,
-                 void* stream);
-int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, void* stream);
+/* contiguous [B, C, T] (TS_F32, TS_BF16 or TS_F16) -> 16-bit rows [B, C, pitch] of out_dtype TS_BF16 / TS_F16 (frames
+ * >= min(T, lens[b]) zero; lens may be NULL) -- the MaskedConv1d.mask_fill of the first consumer
+ * (quartznet/blocks.py:158-167) -- and back to f32 */
+int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, const int32_t* lens, void* out, int out_dtype,
+                 int pitch, void* stream);
+int ts_unpack_rows(const void* in, int in_dtype, int pitch, int B, int C, int T, float* out, void* stream);
 /* MaskedConv1d.get_seq_len (quartznet/blocks.py:142-156) on i32 lengths; i64 <-> i32 conversions */
 int ts_conv_lengths(const int32_t* in, int32_t* out, int B, int K, int S, int D, int P, void* stream);
 int ts_lengths_to_i32(const int64_t* in, int32_t* out, int B, void* stream);

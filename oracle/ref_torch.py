@@ -103,6 +103,60 @@ def encoder(x, lengths, cfgs: List[R.BlockCfg], st, train: bool = False, store=N
     return x, lengths
 
 
+def _fold_bn(st, p):
+    """eval BatchNorm1d(eps=1e-3) as a per-channel affine (quartznet/blocks.py:222-228)."""
+    s = st[p + ".weight"] / torch.sqrt(st[p + ".running_var"] + 1e-3)
+    return s, st[p + ".bias"] - st[p + ".running_mean"] * s
+
+
+def rounder(fmt):
+    """Storage-format model: ``None``/"f32" = identity, "bf16"/"fp16" = round to that format and back."""
+    if fmt in (None, "f32"):
+        return lambda t: t
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[fmt]
+    return lambda t: t.to(dt).to(torch.float32)
+
+
+def block_storage(x, lengths, cfg: R.BlockCfg, st, prefix: str, fmt="bf16"):
+    """Eval-mode block (quartznet/blocks.py:317-338 / citrinet/blocks.py:177-197) with a 16-bit STORAGE format simulated at
+    exactly the four places per sub-block where ANY 16-bit tensor-core implementation must round: the depthwise taps, the
+    depthwise output (GEMM operand), the BN-folded pointwise / residual weights (GEMM operand) and the sub-block output
+    (and, for Citrinet, the pre-gate tensor the SqueezeExcite scale is applied to).  Everything between two roundings is
+    fp32, like the accumulators of the device path.  With ``fmt=None`` this is algebraically the reference block (BN
+    folded).  It is the yardstick that separates what the FORMAT costs at depth from what the kernels add."""
+    q = rounder(fmt)
+    out, out_len = x, lengths
+    strides = cfg.sub_strides()
+    for r in range(cfg.repeat):
+        i = cfg.mconv_index(r)
+        s, k = strides[r], cfg.kernel_size
+        pad = R.get_same_padding(k, s, cfg.dilation)
+        if cfg.separable:
+            out = F.conv1d(_mask(out, out_len), q(st[f"{prefix}mconv.{i}.conv.weight"]), None, s, pad, cfg.dilation,
+                           groups=out.shape[1])
+            out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
+            sc, sh = _fold_bn(st, f"{prefix}mconv.{i + 2}.layer.0")
+            w = q(st[f"{prefix}mconv.{i + 1}.conv.weight"] * sc[:, None, None])
+            out = F.conv1d(_mask(q(out), out_len), w) + sh[None, :, None]
+        else:
+            sc, sh = _fold_bn(st, f"{prefix}mconv.{i + 1}.layer.0")
+            w = q(st[f"{prefix}mconv.{i}.conv.weight"] * sc[:, None, None])
+            out = F.conv1d(_mask(out, out_len), w, None, s, pad, cfg.dilation) + sh[None, :, None]
+            out_len = torch.div(out_len + 2 * pad - cfg.dilation * (k - 1) - 1, s, rounding_mode="floor") + 1
+        if r != cfg.repeat - 1:
+            out = q(F.relu(out))
+    if cfg.kind == "citrinet":
+        i_se = cfg.mconv_index(cfg.repeat - 1) + (3 if cfg.separable else 2)
+        y = out.mean(-1)
+        y = F.relu(y @ st[f"{prefix}mconv.{i_se}.layer.0.fc.0.weight"].T) @ st[f"{prefix}mconv.{i_se}.layer.0.fc.2.weight"].T
+        out = q(out) * torch.sigmoid(y).unsqueeze(-1)
+    if cfg.residual:
+        sc, sh = _fold_bn(st, f"{prefix}res.1.layer.0")
+        w = q(st[f"{prefix}res.0.conv.weight"] * sc[:, None, None])
+        out = out + F.conv1d(_mask(x, lengths), w, None, cfg.residual_stride()) + sh[None, :, None]
+    return q(F.relu(out)), out_len
+
+
 def ctc_loss(logits: torch.Tensor, y: torch.Tensor, prob_lengths: torch.Tensor, y_lengths: torch.Tensor,
              blank_idx: int) -> torch.Tensor:
     """calculate_ctc (src/thunder/ctc_loss.py:15-47): permute -> log_softmax -> F.ctc_loss(mean, zero_infinity)."""

@@ -219,6 +219,22 @@ out = sharded_predict(fake_predict, audio)
 assert out == ["utt%d" % i for i in range(7)], out
 lo, hi = shard_bounds(7, 2, dist.get_rank())
 assert calls == [hi - lo]
+# strong-scaling serving loop: every rank streams ITS slice of each batch, transcripts gathered once at the end
+from thunder_speech_b200.parallel import sharded_predict_stream
+class FakeModule:
+    def __init__(self): self.seen = []
+    def predict_stream(self, batches, depth=3):
+        for xb in batches:
+            self.seen.append(xb.shape[0])
+            yield ["utt%d" % int(r[0].item() // 4) for r in xb]
+fm = FakeModule()
+batches = [audio, audio.flip(0), audio[:5]]
+got = sharded_predict_stream(fm, iter(batches))
+assert got == [["utt%d" % i for i in range(7)], ["utt%d" % i for i in reversed(range(7))], ["utt%d" % i for i in range(5)]], got
+assert fm.seen == [hi - lo, hi - lo, shard_bounds(5, 2, dist.get_rank())[1] - shard_bounds(5, 2, dist.get_rank())[0]]
+fm2 = FakeModule()
+mine = [b[slice(*shard_bounds(b.shape[0], 2, dist.get_rank()))] for b in batches]
+assert sharded_predict_stream(fm2, iter(mine), presharded=True) == got
 dist.barrier(); dist.destroy_process_group()
 print("rank", sys.argv[3], "ok")
 """
@@ -314,10 +330,17 @@ def test_product_code_never_touches_the_oracle_or_the_reference():
     bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
     hits = [m.start() for m in pat.finditer(bench)]
     assert hits, "bench.py must time the oracle port as its cpu_baseline"
-    start = bench.index("def cpu_port_rate")
+    start = bench.index("def cpu_reference_rate")
     end = bench.index("\ndef ", start + 1)
-    assert all(start < h < end for h in hits), "oracle imported outside bench.py cpu_port_rate()"
+    assert all(start < h < end for h in hits), "oracle imported outside bench.py cpu_reference_rate()"
     assert "/root/reference" not in bench
+    # the unmodified reference (baseline/_ref, git-ignored) is only ever reached through baseline/ref_harness.py, and
+    # only from bench.py's reference arms
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+                assert "ref_harness" not in src and "baseline" not in src.replace("cpu_baseline", ""), fn
 
 
 def test_error_rate_metrics_match_levenshtein_definition():

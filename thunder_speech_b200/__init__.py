@@ -12,4 +12,38 @@ Public surface mirrors the reference's module names for this path only:
 All arithmetic runs in ``libthunder_b200.so`` (hand-written CUDA, C ABI in include/thunder_b200.h) through the
 ``torch.ops.thunder_b200.*`` custom ops; there is no CPU or eager fallback.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+import os as _os
+
+#: storage format of the activation rows / GEMM operands of the INFERENCE path: "bf16" (default; the reference's autocast
+#: type, 8-bit mantissa, fp32 range) or "fp16" (IEEE half: 11-bit mantissa, conversions saturate at +-65504).  Same kernels,
+#: same bytes, same tensor-core rate (tcgen05 kind::f16 takes either); fp16 rows are what holds the 2e-2 logit parity
+#: against the fp32 reference through the 90 convolutions of QuartzNet 15x5 (DESIGN.md section 2).  The training step
+#: always runs bf16.
+_PRECISIONS = ("bf16", "fp16")
+_default_precision = _os.environ.get("THUNDER_B200_PRECISION", "bf16")
+if _default_precision not in _PRECISIONS:
+    raise ValueError(f"THUNDER_B200_PRECISION must be one of {_PRECISIONS}, got {_default_precision!r}")
+
+
+def set_default_precision(precision: str) -> None:
+    """Row format used by modules that were not given one explicitly (``CTCModule.set_precision``)."""
+    global _default_precision
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}, got {precision!r}")
+    _default_precision = precision
+
+
+def get_default_precision() -> str:
+    return _default_precision
+
+
+def row_dtype(precision=None):
+    """torch dtype of the activation rows for ``precision`` (None = the package default)."""
+    import torch
+
+    precision = precision or _default_precision
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}, got {precision!r}")
+    return torch.float16 if precision == "fp16" else torch.bfloat16

@@ -21,7 +21,10 @@ TS_F32 = 0
 TS_BF16 = 1
 TS_I16 = 2
 TS_FIX32 = 3
+TS_F16 = 4
 TS_DW_INPUT_PREMASKED = 1
+TS_ROWS_F16 = 2
+TS_PW_RELU = 1
 
 _lib = None
 
@@ -87,8 +90,8 @@ SIGNATURES = {
     "ts_ctc_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float,
                             c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ts_gather_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "ts_pack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "ts_unpack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ts_pack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ts_unpack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ts_conv_lengths": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ts_lengths_to_i32": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "ts_lengths_to_i64": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -37,7 +37,9 @@ class SqueezeExcite(nn.Module):
             pool = x.float().sum(-1).contiguous()
             gate = ops.se_fc(pool, T, self.fc[0].weight.detach().float().contiguous(),
                              self.fc[2].weight.detach().float().contiguous())
-            rows = ops.pack_rows(x)
+            from .. import row_dtype
+
+            rows = ops.pack_rows(x, None, row_dtype() == torch.float16)
             return ops.unpack_rows(ops.se_apply(rows, gate, None, False), T)
 
 

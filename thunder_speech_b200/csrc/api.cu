@@ -17,24 +17,39 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static std::atomic<int> g_opt_dw_mma{1};
-static std::atomic<int> g_opt_pw_big{1};
-static std::atomic<int> g_opt_dw_tma{1};
-static std::atomic<int> g_opt_pw_bn{0};
-static std::atomic<int> g_opt_pdl{3};
-int option_pdl() { return g_opt_pdl.load(std::memory_order_relaxed); }
-static std::atomic<int> g_opt_pw_pair{2};
-int option_pw_pair() { return g_opt_pw_pair.load(std::memory_order_relaxed); }
-int option_pw_bn() { return g_opt_pw_bn.load(std::memory_order_relaxed); }
-static std::atomic<int> g_opt_dw_base_offset{0};
-static std::atomic<int> g_opt_dw_share_halo{1};
-static std::atomic<int> g_opt_dw_pro{30};
-int option_dw_pro() { return g_opt_dw_pro.load(std::memory_order_relaxed); }
-int option_dw_share_halo() { return g_opt_dw_share_halo.load(std::memory_order_relaxed); }
-int option_dw_tma() { return g_opt_dw_tma.load(std::memory_order_relaxed); }
-int option_dw_base_offset() { return g_opt_dw_base_offset.load(std::memory_order_relaxed); }
-int option_dw_mma() { return g_opt_dw_mma.load(std::memory_order_relaxed); }
-int option_pw_big() { return g_opt_pw_big.load(std::memory_order_relaxed); }
+// runtime switches (ts_set_option / THUNDER_B200_OPTIONS), one table so that adding an A/B knob is one line
+struct Option { const char* name; std::atomic<int> value; };
+static Option g_options[] = {
+    {"dw_mma", {1}},          // stride-1 depthwise convs on the tensor cores
+    {"pw_big", {1}},          // persistent 256-wide GEMM tiles for 16-bit outputs with Cout > 128
+    {"dw_tma", {1}},          // TMA-fed Toeplitz kernel for pre-masked rows
+    {"pw_bn", {0}},
+    {"pdl", {3}},             // programmatic dependent launch: bit 0 inference kernels, bit 1 training kernels
+    {"pw_pair", {2}},         // CTA-pair GEMM: 1 = only K >= 1024, 2 = every 16-bit-row GEMM with Cout > 128
+    {"dw_base_offset", {0}},
+    {"dw_share_halo", {1}},
+    {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
+    {"serpentine", {1}},      // alternate the utterance walk direction between consecutive launches (L2 reuse)
+    {"dbg", {0}},             // scratch knob for experiments
+};
+static std::atomic<int>& opt(const char* name) {
+  for (auto& o : g_options)
+    if (strcmp(o.name, name) == 0) return o.value;
+  return g_options[sizeof(g_options) / sizeof(g_options[0]) - 1].value;
+}
+int option_pdl() { return opt("pdl").load(std::memory_order_relaxed); }
+int option_pw_pair() { return opt("pw_pair").load(std::memory_order_relaxed); }
+int option_pw_bn() { return opt("pw_bn").load(std::memory_order_relaxed); }
+int option_dw_pro() { return opt("dw_pro").load(std::memory_order_relaxed); }
+int option_dw_share_halo() { return opt("dw_share_halo").load(std::memory_order_relaxed); }
+int option_dw_tma() { return opt("dw_tma").load(std::memory_order_relaxed); }
+int option_dw_base_offset() { return opt("dw_base_offset").load(std::memory_order_relaxed); }
+int option_dw_mma() { return opt("dw_mma").load(std::memory_order_relaxed); }
+int option_pw_big() { return opt("pw_big").load(std::memory_order_relaxed); }
+int option_serpentine() { return opt("serpentine").load(std::memory_order_relaxed); }
+int option_dbg() { return opt("dbg").load(std::memory_order_relaxed); }
+static std::atomic<unsigned> g_walk{0};
+int next_walk_reversed() { return option_serpentine() ? (int)(g_walk.fetch_add(1, std::memory_order_relaxed) & 1u) : 0; }
 
 }  // namespace ts
 
@@ -44,42 +59,12 @@ extern "C" int64_t ts_launch_count(void) { return ts::g_launches.load(std::memor
 extern "C" int ts_row_pitch(int T) { return T <= 0 ? 0 : ts::round_up(T, ts::kRowPitchAlign); }
 
 extern "C" int ts_set_option(const char* name, int value) {
-  if (name != nullptr && strcmp(name, "dw_mma") == 0) {
-    ts::g_opt_dw_mma.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "pdl") == 0) {
-    ts::g_opt_pdl.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "pw_pair") == 0) {
-    ts::g_opt_pw_pair.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "pw_bn") == 0) {
-    ts::g_opt_pw_bn.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "dw_tma") == 0) {
-    ts::g_opt_dw_tma.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "dw_base_offset") == 0) {
-    ts::g_opt_dw_base_offset.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "dw_pro") == 0) {
-    ts::g_opt_dw_pro.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "dw_share_halo") == 0) {
-    ts::g_opt_dw_share_halo.store(value);
-    return TS_OK;
-  }
-  if (name != nullptr && strcmp(name, "pw_big") == 0) {
-    ts::g_opt_pw_big.store(value);
-    return TS_OK;
-  }
+  if (name != nullptr)
+    for (auto& o : ts::g_options)
+      if (strcmp(o.name, name) == 0) {
+        o.value.store(value);
+        return TS_OK;
+      }
   ts::set_error("ts_set_option: unknown option '%s'", name ? name : "(null)");
   return TS_ERR_INVALID;
 }

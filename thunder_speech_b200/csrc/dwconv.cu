@@ -48,7 +48,7 @@ template <int K, int S, int D>
 __global__ void __launch_bounds__(WARPS * 32)
 dw_fast_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_in, const float* __restrict__ w,
                const int32_t* __restrict__ len_in, __nv_bfloat16* __restrict__ y, int T_out, int pitch_out, int segs,
-               int items) {
+               int items, int f16) {
   using G = Geo<K, S, D>;
   extern __shared__ __align__(16) float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,8 +75,9 @@ dw_fast_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_i
       const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        v[2 * h] = (t + 2 * h < lin) ? __uint_as_float(q[h] << 16) : 0.f;
-        v[2 * h + 1] = (t + 2 * h + 1 < lin) ? __uint_as_float(q[h] & 0xFFFF0000u) : 0.f;
+        const float2 f = unpack16x2(q[h], f16 != 0);
+        v[2 * h] = (t + 2 * h < lin) ? f.x : 0.f;
+        v[2 * h + 1] = (t + 2 * h + 1 < lin) ? f.y : 0.f;
       }
     } else {
 #pragma unroll
@@ -122,8 +123,7 @@ dw_fast_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_i
     for (int h = 0; h < 4; ++h) {
       const float lo = (to + 2 * h < lout) ? acc[2 * h] : 0.f;
       const float hi = (to + 2 * h + 1 < lout) ? acc[2 * h + 1] : 0.f;
-      __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
-      o[h] = *reinterpret_cast<uint32_t*>(&pr);
+      o[h] = pack16x2(lo, hi, f16 != 0);
     }
     *reinterpret_cast<uint4*>(y + (size_t)row * pitch_out + to) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -133,7 +133,7 @@ dw_fast_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_i
 __global__ void dw_generic_kernel(const __nv_bfloat16* __restrict__ x, int C, int T_in, int pitch_in,
                                   const float* __restrict__ w, int K, int S, int D, int P,
                                   const int32_t* __restrict__ len_in, __nv_bfloat16* __restrict__ y, int T_out,
-                                  int pitch_out, int rows) {
+                                  int pitch_out, int rows, int f16) {
   const int t = blockIdx.y * blockDim.x + threadIdx.x;
   const int row = blockIdx.x;
   if (t >= pitch_out || row >= rows) return;
@@ -147,15 +147,16 @@ __global__ void dw_generic_kernel(const __nv_bfloat16* __restrict__ x, int C, in
     const float* wr = w + (size_t)c * K;
     for (int k = 0; k < K; ++k) {
       const int ti = t * S - P + k * D;
-      if (ti >= 0 && ti < lin) acc = fmaf(wr[k], __bfloat162float(xrow[ti]), acc);
+      if (ti >= 0 && ti < lin)
+        acc = fmaf(wr[k], unpack16(reinterpret_cast<const uint16_t*>(xrow)[ti], f16 != 0), acc);
     }
   }
-  y[(size_t)row * pitch_out + t] = __float2bfloat16_rn(acc);
+  reinterpret_cast<uint16_t*>(y)[(size_t)row * pitch_out + t] = pack16(acc, f16 != 0);
 }
 
 template <int K, int S, int D>
 int launch_fast(const __nv_bfloat16* x, int B, int C, int T_in, int pitch_in, const float* w, const int32_t* len_in,
-                __nv_bfloat16* y, int T_out, int pitch_out, cudaStream_t st) {
+                __nv_bfloat16* y, int T_out, int pitch_out, cudaStream_t st, int f16) {
   using G = Geo<K, S, D>;
   const int segs = ceil_div(pitch_out, SEG);
   const long long items_ll = (long long)B * C * segs;
@@ -169,7 +170,7 @@ int launch_fast(const __nv_bfloat16* x, int B, int C, int T_in, int pitch_in, co
     attr_set = true;
   }
   kern<<<ceil_div(items, WARPS), WARPS * 32, smem, st>>>(x, C, T_in, pitch_in, w, len_in, y, T_out, pitch_out, segs,
-                                                         items);
+                                                         items, f16);
   TS_LAUNCH_CHECK("dw_fast_kernel");
   return TS_OK;
 }
@@ -181,13 +182,13 @@ namespace ts {
 int launch_dw_mma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
 int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
-                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st);
+                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16);
 }
 using namespace ts;
 
 #define TS_DW_CASE(KK, SS, DD)                                                                            \
   if (K == KK && S == SS && D == DD && P == dw::same_pad(KK, SS, DD))                                     \
-    return dw::launch_fast<KK, SS, DD>(xb, B, C, T_in, pitch_in, w, len_in, yb, T_out, pitch_out, st);
+    return dw::launch_fast<KK, SS, DD>(xb, B, C, T_in, pitch_in, w, len_in, yb, T_out, pitch_out, st, f16);
 
 extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float* w, int K, int S, int D,
                           int P, const int32_t* len_in, int flags, void* y, int pitch_out, void* stream) {
@@ -203,13 +204,14 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
+  const int f16 = (flags & TS_ROWS_F16) ? 1 : 0;
   // stride-1 / dilation-1 / odd-K "same" convolutions: Toeplitz MMA on the tensor cores (dwmma.cu)
   // ... through TMA when the caller guarantees rows are already zero beyond len_in (or there are no lengths)
   if (S == 1 && option_dw_mma() && option_dw_tma() && (len_in == nullptr || (flags & TS_DW_INPUT_PREMASKED))) {
-    const int rc = launch_dw_tma(xb, B, C, T_in, pitch_in, w, K, D, P, len_in, yb, pitch_out, st);
+    const int rc = launch_dw_tma(xb, B, C, T_in, pitch_in, w, K, D, P, len_in, yb, pitch_out, st, f16);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
   }
-  if (S == 1 && D == 1 && option_dw_mma()) {
+  if (S == 1 && D == 1 && option_dw_mma() && !f16) {   // (the cp.async predecessor is bf16 only)
     const int rc = launch_dw_mma(xb, B, C, T_in, pitch_in, w, K, P, len_in, yb, pitch_out, st);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
   }
@@ -224,7 +226,8 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   // generic
   const int rows = B * C;
   dim3 grid(rows, ceil_div(pitch_out, 128));
-  dw::dw_generic_kernel<<<grid, 128, 0, st>>>(xb, C, T_in, pitch_in, w, K, S, D, P, len_in, yb, T_out, pitch_out, rows);
+  dw::dw_generic_kernel<<<grid, 128, 0, st>>>(xb, C, T_in, pitch_in, w, K, S, D, P, len_in, yb, T_out, pitch_out, rows,
+                                              f16);
   TS_LAUNCH_CHECK("dw_generic_kernel");
   return TS_OK;
 }

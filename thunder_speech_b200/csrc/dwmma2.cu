@@ -11,6 +11,7 @@
 #include "ts_common.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
+#include <type_traits>
 
 namespace ts {
 namespace dwt2 {
@@ -35,6 +36,8 @@ struct Params {
   int W, R, NB;
   int HL, NQ;            // left halo windows = ceil(P / 64); Toeplitz blocks = HL + 1 + (63 + P) / 64
   int tiles_per_chan, tiles_per_cta;
+  int f16;               // rows (and the Toeplitz blocks) are IEEE fp16 instead of bf16
+  int rev;               // walk the utterance tiles from the far end (see next_walk_reversed())
   int base_offset_mode;  // experiment switch, default 0: MEASURED on B200 -- a SW128 tile whose start is shifted by
                          // q*128 B is addressed correctly with base-offset 0 (the XOR uses absolute address bits);
                          // writing q into bits 49..51 gives wrong results
@@ -92,6 +95,8 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   const int c = blockIdx.x;
   const int tile0 = blockIdx.y * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.tiles_per_chan - tile0);
+  // n-th tile of this CTA; reversed walks start at the last utterances (CTAs with a low blockIdx.y are scheduled first)
+  auto tile_at = [&](int n) { return p.rev ? p.tiles_per_chan - 1 - (tile0 + n) : tile0 + n; };
   const uint32_t box_bytes = (uint32_t)(128 * p.R * p.NB);
 
   if (warp == 0 && lane == 0) {
@@ -132,13 +137,13 @@ dw_tma_kernel(const __grid_constant__ Params p) {
         const int s = n % NSTAGE;
         ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&full_bar[s], box_bytes);
-        tma_load_4d(sA + s * A_STAGE, &p.in, &full_bar[s], 0, -p.HL, c, (tile0 + n) * p.NB);
+        tma_load_4d(sA + s * A_STAGE, &p.in, &full_bar[s], 0, -p.HL, c, tile_at(n) * p.NB);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(MROWS, L, 0, 0);
+      const uint32_t idesc = ptx::umma_idesc_16(MROWS, L, 0, 0, p.f16);
       const uint32_t sb = ptx::smem_u32(sB);
       const int jlo = 64 * p.HL - p.P, jhi = 64 * p.HL + 63 + p.P;  // non-zero band of the stacked Toeplitz rows
       ptx::mbar_wait(b_ready, 0);
@@ -190,8 +195,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
           fa = (da >= 0 && da < kd && da % p.D == 0) ? wc[da / p.D] : 0.f;
           fb = (db >= 0 && db < kd && db % p.D == 0) ? wc[db / p.D] : 0.f;
         }
-        __nv_bfloat162 pr = __floats2bfloat162_rn(fa, fb);
-        pk[h] = *reinterpret_cast<uint32_t*>(&pr);
+        pk[h] = pack16x2(fa, fb, p.f16 != 0);
       }
       *reinterpret_cast<uint4*>(sB + q * BQ + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -208,7 +212,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     pdl_wait();                // no global write of this grid may overtake the previous grid's reads
     for (int n = 0; n < ntiles; ++n) {
       const int a = n % ACC_STAGES;
-      const int b0 = (tile0 + n) * p.NB;
+      const int b0 = tile_at(n) * p.NB;
       const int b = b0 + bl;
       int lout = p.T;
       if (p.lens && bl < p.NB && b < p.B) lout = min(lout, max(__ldg(p.lens + b), 0));
@@ -225,24 +229,30 @@ dw_tma_kernel(const __grid_constant__ Params p) {
       if (tid == 128) bulk_wait_read0();
       named_bar_sync(1, 128);
       const bool interior = t + 64 <= lout;
+      auto pack_and_stage = [&](auto f16_tag) {   // uniform branch on the row format: one conversion per pair on each path
+        constexpr bool kF16 = decltype(f16_tag)::value;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint32_t pk[4];
+        for (int g = 0; g < 8; ++g) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int e = g * 8 + 2 * h;
-          float lo = __uint_as_float(v[e]), hi = __uint_as_float(v[e + 1]);
-          if (!interior) {
-            if (t + e >= lout) lo = 0.f;
-            if (t + e + 1 >= lout) hi = 0.f;
+          for (int h = 0; h < 4; ++h) {
+            const int e = g * 8 + 2 * h;
+            float lo = __uint_as_float(v[e]), hi = __uint_as_float(v[e + 1]);
+            if (!interior) {
+              if (t + e >= lout) lo = 0.f;
+              if (t + e + 1 >= lout) hi = 0.f;
+            }
+            pk[h] = kF16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
           }
-          __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
-          pk[h] = *reinterpret_cast<uint32_t*>(&pr);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ (row & 7)) << 4)), "r"(pk[0]),
+                       "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ (row & 7)) << 4)), "r"(pk[0]),
-                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                     : "memory");
-      }
+      };
+      if (p.f16)
+        pack_and_stage(std::true_type{});
+      else
+        pack_and_stage(std::false_type{});
       fence_proxy_async();
       named_bar_sync(1, 128);
       if (tid == 128) {
@@ -267,13 +277,14 @@ int option_dw_share_halo();
 int option_dw_pro();
 
 int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
-                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st) {
+                  const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16) {
   // stride 1, length preserving ("same") padding: 2 P == D (K - 1)
   if (!(2 * P == D * (K - 1) && D >= 1 && pitch_in == pitch_out && pitch_in % 64 == 0 && C <= 65535))
     return TS_ERR_UNSUPPORTED;
   dwt2::Params p;
   memset(&p, 0, sizeof(p));
-  p.w = w; p.lens = lens;
+  p.rev = next_walk_reversed();
+  p.w = w; p.lens = lens; p.f16 = f16;
   p.B = B; p.C = C; p.T = T; p.K = K; p.P = P; p.D = D;
   p.W = pitch_in / 64;
   p.HL = ceil_div(P, 64);

@@ -291,6 +291,7 @@ logmel_kernel(const float* __restrict__ audio, int B, int N, int F, int hop, flo
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(v); }
 
 constexpr int NORM_WARPS = 8;
 constexpr int NORM_REG = 64;  // values per lane kept in registers => F <= 2048 single pass
@@ -411,13 +412,16 @@ extern "C" int ts_feature_normalize(const float* logmel, const int64_t* lengths,
   TS_REQUIRE(logmel && lengths && out, TS_ERR_INVALID, "ts_feature_normalize: null pointer");
   TS_REQUIRE(B > 0 && nfilt > 0 && F > 0 && hop > 0, TS_ERR_INVALID, "ts_feature_normalize: bad sizes");
   TS_REQUIRE(out_pitch >= F, TS_ERR_INVALID, "ts_feature_normalize: out_pitch %d < F %d", out_pitch, F);
-  TS_REQUIRE(out_dtype == TS_F32 || out_dtype == TS_BF16, TS_ERR_INVALID, "ts_feature_normalize: bad dtype %d",
-             out_dtype);
+  TS_REQUIRE(out_dtype == TS_F32 || out_dtype == TS_BF16 || out_dtype == TS_F16, TS_ERR_INVALID,
+             "ts_feature_normalize: bad dtype %d", out_dtype);
   const int rows = B * nfilt;
   const int grid = ceil_div(rows, feat::NORM_WARPS);
   if (out_dtype == TS_F32) {
     feat::normalize_rows_kernel<float><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
         logmel, lengths, rows, nfilt, F, hop, div_guard, (float*)out, out_pitch, seq_len_out);
+  } else if (out_dtype == TS_F16) {
+    feat::normalize_rows_kernel<__half><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        logmel, lengths, rows, nfilt, F, hop, div_guard, (__half*)out, out_pitch, seq_len_out);
   } else {
     feat::normalize_rows_kernel<__nv_bfloat16><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
         logmel, lengths, rows, nfilt, F, hop, div_guard, (__nv_bfloat16*)out, out_pitch, seq_len_out);

@@ -7,27 +7,28 @@ namespace misc {
 
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ld_as_float(const __half* p) { return __half2float(*p); }
 
 // [B, C, T] (contiguous, f32 or bf16) -> bf16 rows [B, C, pitch]; frames t >= min(T, lens[b]) are zero-filled.
 template <typename InT>
-__global__ void pack_rows_kernel(const InT* __restrict__ in, int T, __nv_bfloat16* __restrict__ out, int pitch,
-                                 long long rows, int C, const int32_t* __restrict__ lens) {
+__global__ void pack_rows_kernel(const InT* __restrict__ in, int T, uint16_t* __restrict__ out, int pitch,
+                                 long long rows, int C, const int32_t* __restrict__ lens, int f16) {
   const long long row = blockIdx.x;
   const int t = blockIdx.y * blockDim.x + threadIdx.x;
   if (row >= rows || t >= pitch) return;
   int lim = T;
   if (lens != nullptr) lim = min(lim, lens[row / C]);  // MaskedConv1d.mask_fill of the consumer (quartznet/blocks.py:158-167)
   const float v = (t < lim) ? ld_as_float(in + row * T + t) : 0.f;
-  out[row * pitch + t] = __float2bfloat16_rn(v);
+  out[row * pitch + t] = pack16(v, f16 != 0);
 }
 
-// bf16 rows [B, C, pitch] -> contiguous f32 [B, C, T]
-__global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ in, int pitch, float* __restrict__ out, int T,
-                                   long long rows) {
+// 16-bit rows [B, C, pitch] -> contiguous f32 [B, C, T]
+__global__ void unpack_rows_kernel(const uint16_t* __restrict__ in, int pitch, float* __restrict__ out, int T,
+                                   long long rows, int f16) {
   const long long row = blockIdx.x;
   const int t = blockIdx.y * blockDim.x + threadIdx.x;
   if (row >= rows || t >= T) return;
-  out[row * T + t] = __bfloat162float(in[row * pitch + t]);
+  out[row * T + t] = unpack16(in[row * pitch + t], f16 != 0);
 }
 
 // out[b] = clamp-free MaskedConv1d.get_seq_len (quartznet/blocks.py:142-156): floor((L + 2p - d(k-1) - 1)/s) + 1
@@ -141,7 +142,7 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int C, i
 // out = relu(gate[b, c] * y1[b, c, t]), frames t >= lens[b] stored as zero when lens is given.  8 frames per thread.
 __global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ y1, const float* __restrict__ gate, int C, int pitch,
                                 const int32_t* __restrict__ lens, int relu, __nv_bfloat16* __restrict__ out,
-                                long long rows) {
+                                long long rows, int f16) {
   const long long row = blockIdx.x;
   const int t = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (row >= rows || t >= pitch) return;
@@ -152,12 +153,12 @@ __global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ y1, const floa
   uint32_t o[4];
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
-    float lo = g * __uint_as_float(w[h] << 16), hi = g * __uint_as_float(w[h] & 0xFFFF0000u);
+    const float2 f = unpack16x2(w[h], f16 != 0);
+    float lo = g * f.x, hi = g * f.y;
     if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
     if (t + 2 * h >= lim) lo = 0.f;
     if (t + 2 * h + 1 >= lim) hi = 0.f;
-    __nv_bfloat162 pr = __floats2bfloat162_rn(lo, hi);
-    o[h] = *reinterpret_cast<uint32_t*>(&pr);
+    o[h] = pack16x2(lo, hi, f16 != 0);
   }
   *reinterpret_cast<uint4*>(out + row * pitch + t) = make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -237,29 +238,37 @@ ctc_collapse_kernel(const int64_t* __restrict__ ids, int T, int64_t* __restrict_
 using namespace ts;
 
 extern "C" int ts_pack_rows(const void* in, int in_dtype, int B, int C, int T, const int32_t* lens, void* out,
-                            int pitch, void* stream) {
+                            int out_dtype, int pitch, void* stream) {
   TS_REQUIRE(in && out, TS_ERR_INVALID, "ts_pack_rows: null pointer");
+  TS_REQUIRE(out_dtype == TS_BF16 || out_dtype == TS_F16, TS_ERR_INVALID, "ts_pack_rows: rows are TS_BF16 or TS_F16");
+  const int f16 = out_dtype == TS_F16;
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_pack_rows: bad sizes");
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_pack_rows: too many rows");
   dim3 grid((unsigned)rows, ceil_div(pitch, 256));
   if (in_dtype == TS_F32)
-    misc::pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, T, (__nv_bfloat16*)out, pitch, rows, C, lens);
-  else
+    misc::pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, T, (uint16_t*)out, pitch, rows, C, lens, f16);
+  else if (in_dtype == TS_BF16)
     misc::pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, T,
-                                                                                  (__nv_bfloat16*)out, pitch, rows, C,
-                                                                                  lens);
+                                                                                  (uint16_t*)out, pitch, rows, C, lens, f16);
+  else if (in_dtype == TS_F16)
+    misc::pack_rows_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, T, (uint16_t*)out, pitch,
+                                                                           rows, C, lens, f16);
+  else
+    TS_REQUIRE(false, TS_ERR_INVALID, "ts_pack_rows: bad input dtype %d", in_dtype);
   TS_LAUNCH_CHECK("pack_rows_kernel");
   return TS_OK;
 }
 
-extern "C" int ts_unpack_rows(const void* in, int pitch, int B, int C, int T, float* out, void* stream) {
+extern "C" int ts_unpack_rows(const void* in, int in_dtype, int pitch, int B, int C, int T, float* out, void* stream) {
   TS_REQUIRE(in && out, TS_ERR_INVALID, "ts_unpack_rows: null pointer");
+  TS_REQUIRE(in_dtype == TS_BF16 || in_dtype == TS_F16, TS_ERR_INVALID, "ts_unpack_rows: rows are TS_BF16 or TS_F16");
   TS_REQUIRE(B > 0 && C > 0 && T > 0 && pitch >= T, TS_ERR_INVALID, "ts_unpack_rows: bad sizes");
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_unpack_rows: too many rows");
   dim3 grid((unsigned)rows, ceil_div(T, 256));
-  misc::unpack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, pitch, out, T, rows);
+  misc::unpack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in, pitch, out, T, rows,
+                                                                   in_dtype == TS_F16);
   TS_LAUNCH_CHECK("unpack_rows_kernel");
   return TS_OK;
 }
@@ -338,15 +347,16 @@ extern "C" int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_i
   return TS_OK;
 }
 
-extern "C" int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int relu,
+extern "C" int ts_se_apply(const void* y1, const float* gate, int B, int C, int pitch, const int32_t* lens, int flags,
                            void* out, void* stream) {
+  const int relu = flags & TS_PW_RELU;
   TS_REQUIRE(y1 && gate && out, TS_ERR_INVALID, "ts_se_apply: null pointer");
   TS_REQUIRE(B > 0 && C > 0 && pitch > 0 && pitch % 8 == 0, TS_ERR_INVALID, "ts_se_apply: bad sizes");
   const long long rows = (long long)B * C;
   TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_se_apply: too many rows");
   dim3 grid((unsigned)rows, ceil_div(pitch / 8, 128));
   misc::se_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y1, gate, C, pitch, lens, relu,
-                                                                (__nv_bfloat16*)out, rows);
+                                                                (__nv_bfloat16*)out, rows, (flags & TS_ROWS_F16) ? 1 : 0);
   TS_LAUNCH_CHECK("se_apply_kernel");
   return TS_OK;
 }

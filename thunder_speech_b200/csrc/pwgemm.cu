@@ -51,6 +51,7 @@ struct Params {
   const float* se_scale;       // SE excite:  [B, Cout] sigmoid gate applied to y1 before the residual add
   const __nv_bfloat16* y1;     // main-branch output [B, Cout, y1_pitch] read by the SE-apply epilogue
   int y1_pitch;
+  int f16;                     // operands / 16-bit output rows are IEEE fp16 instead of bf16
 };
 
 template <int BN>
@@ -117,7 +118,7 @@ pw_gemm_kernel(const __grid_constant__ Params p) {
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer (single thread) =====
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, /*a_mn_major=*/0, /*b_mn_major=*/1);
+    const uint32_t idesc = ptx::umma_idesc_16(BM, BN, /*a_mn_major=*/0, /*b_mn_major=*/1, p.f16);
     for (int kc = 0; kc < num_k; ++kc) {
       const int s = kc % T::kStages;
       const uint32_t phase = (kc / T::kStages) & 1;
@@ -171,10 +172,9 @@ pw_gemm_kernel(const __grid_constant__ Params p) {
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const float lo = __uint_as_float(w[h] << 16);
-            const float hi = __uint_as_float(w[h] & 0xFFFF0000u);
-            r[g * 8 + 2 * h] += gate * lo;
-            r[g * 8 + 2 * h + 1] += gate * hi;
+            const float2 f = unpack16x2(w[h], p.f16 != 0);
+            r[g * 8 + 2 * h] += gate * f.x;
+            r[g * 8 + 2 * h + 1] += gate * f.y;
           }
         }
       }
@@ -199,8 +199,7 @@ pw_gemm_kernel(const __grid_constant__ Params p) {
           uint32_t w[4];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            __nv_bfloat162 pr = __floats2bfloat162_rn(r[g * 8 + 2 * h], r[g * 8 + 2 * h + 1]);
-            w[h] = *reinterpret_cast<uint32_t*>(&pr);
+            w[h] = pack16x2(r[g * 8 + 2 * h], r[g * 8 + 2 * h + 1], p.f16 != 0);
           }
           o[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -228,7 +227,7 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st, float* stats = nullptr);
+                        cudaStream_t st, float* stats = nullptr, int f16 = 0);
 int option_pw_pair();
 }
 using namespace ts;
@@ -250,17 +249,21 @@ extern "C" int ts_pw_gemm_stats(const void* w, const void* x, int cin, int x_pit
 // Host side: see include/thunder_b200.h for the contract.
 extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1,
                           int cin1, int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens,
-                          void* out, int out_dtype, int out_pitch, int relu, int64_t* pool_fixed, const float* se_scale,
+                          void* out, int out_dtype, int out_pitch, int flags, int64_t* pool_fixed, const float* se_scale,
                           const void* y1, int y1_pitch, void* stream) {
   unsigned long long* pool = reinterpret_cast<unsigned long long*>(pool_fixed);
+  const int relu = flags & TS_PW_RELU;
+  const int f16 = (flags & TS_ROWS_F16) ? 1 : 0;
   TS_REQUIRE(w0 && x0 && out, TS_ERR_INVALID, "ts_pw_gemm: null pointer");
   TS_REQUIRE(B > 0 && Cout > 0 && T > 0 && cin0 > 0, TS_ERR_INVALID, "ts_pw_gemm: bad sizes");
   TS_REQUIRE(cin0 % 8 == 0 && (cin1 % 8 == 0), TS_ERR_UNSUPPORTED,
              "ts_pw_gemm: input channels must be multiples of 8 (16-byte TMA rows), got %d / %d", cin0, cin1);
   TS_REQUIRE(x0_pitch % 8 == 0 && x0_pitch >= T && (cin1 == 0 || (x1_pitch % 8 == 0 && x1_pitch >= T)), TS_ERR_INVALID,
              "ts_pw_gemm: activation pitch must be a multiple of 8 frames and >= T");
-  TS_REQUIRE(out_dtype == TS_F32 || out_dtype == TS_BF16, TS_ERR_INVALID, "ts_pw_gemm: bad out dtype");
-  TS_REQUIRE(out_pitch >= T && (out_dtype == TS_F32 || out_pitch % 64 == 0), TS_ERR_INVALID,
+  TS_REQUIRE(out_dtype == TS_F32 || out_dtype == (f16 ? TS_F16 : TS_BF16), TS_ERR_INVALID,
+             "ts_pw_gemm: out dtype must be TS_F32 or the operand format (TS_BF16, or TS_F16 with TS_ROWS_F16)");
+  const bool out16 = out_dtype != TS_F32;
+  TS_REQUIRE(out_pitch >= T && (!out16 || out_pitch % 64 == 0), TS_ERR_INVALID,
              "ts_pw_gemm: bf16 output pitch must be a multiple of 64 frames and >= T (got %d)", out_pitch);
   TS_REQUIRE(!y1 || (y1_pitch % 64 == 0 && se_scale), TS_ERR_INVALID, "ts_pw_gemm: y1 needs se_scale and a 64-multiple pitch");
   TS_REQUIRE((cin1 == 0) == (w1 == nullptr) && (cin1 == 0) == (x1 == nullptr), TS_ERR_INVALID,
@@ -268,13 +271,13 @@ extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch
   TS_REQUIRE(B <= 65535, TS_ERR_UNSUPPORTED, "ts_pw_gemm: B > 65535");
 
   // option pw_pair: 1 = CTA-pair kernel for K >= 1024, 2 = for every bf16-row GEMM with Cout > 128
-  if (out_dtype == TS_BF16 && option_pw_big() && option_pw_pair() > 0 &&
-      (option_pw_pair() >= 2 || cin0 + cin1 >= 1024)) {
+  if (out16 && option_pw_big() && option_pw_pair() > 0 &&
+      (option_pw_pair() >= 2 || cin0 + cin1 >= 1024 || f16)) {
     const int rc = launch_pw_gemm_pair(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out,
-                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream);
+                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream, nullptr, f16);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
   }
-  if (out_dtype == TS_BF16 && option_pw_big()) {
+  if (out16 && !f16 && option_pw_big()) {
     const int rc = launch_pw_gemm_big(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out,
                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
@@ -310,6 +313,7 @@ extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch
   p.se_scale = se_scale;
   p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1);
   p.y1_pitch = y1_pitch;
+  p.f16 = f16;
 
   auto kern = pw::pw_gemm_kernel<BN>;
   constexpr int smem = pw::Tile<BN>::kSmemBytes;

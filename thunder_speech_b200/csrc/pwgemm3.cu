@@ -13,6 +13,7 @@
 #include "ts_common.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
+#include <type_traits>
 
 namespace ts {
 namespace pw3 {
@@ -44,6 +45,8 @@ struct Params {
   const float* se_scale;
   const __nv_bfloat16* y1;
   int y1_pitch;
+  int f16;            // operands and 16-bit output rows are IEEE fp16 instead of bf16
+  int rev;            // walk the (utterance, frame-tile) space from the far end (see next_walk_reversed())
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -175,7 +178,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     // ===== TMA producer: runs ahead over this CTA's whole tile list =====
     uint32_t cnt = 0;
     for (int tile = pair; tile < p.num_tiles; tile += npairs) {
-      const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+      const int mt = tile % p.m_tiles, rest = p.rev ? p.num_tiles / p.m_tiles - 1 - tile / p.m_tiles : tile / p.m_tiles;
       const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
       const int m0 = mt * BM + 128 * (int)rank;          // this CTA's 128 output channels
       const int t0 = nt * BN + (BN / 2) * (int)rank;     // this CTA's half of the frame tile
@@ -200,7 +203,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ===== MMA issuer (leader CTA only) =====
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN, 0, 1);
+    const uint32_t idesc = ptx::umma_idesc_16(256, BN, 0, 1, p.f16);
     uint32_t cnt = 0, it = 0;
     for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
       const int a = it % ACC;
@@ -231,7 +234,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     const uint32_t stg_row = ptx::smem_u32(stg) + lane * 128;
     uint32_t it = 0;
     for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
-      const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+      const int mt = tile % p.m_tiles, rest = p.rev ? p.num_tiles / p.m_tiles - 1 - tile / p.m_tiles : tile / p.m_tiles;
       const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
       const int t0 = nt * BN + h * 128;
       const int mrow0 = mt * BM + (int)rank * 128 + q * 32;
@@ -277,8 +280,9 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int hh = 0; hh < 4; ++hh) {
-                r[g * 8 + 2 * hh] += gate * __uint_as_float(w[hh] << 16);
-                r[g * 8 + 2 * hh + 1] += gate * __uint_as_float(w[hh] & 0xFFFF0000u);
+                const float2 f = unpack16x2(w[hh], p.f16 != 0);
+                r[g * 8 + 2 * hh] += gate * f.x;
+                r[g * 8 + 2 * hh + 1] += gate * f.y;
               }
             }
           }
@@ -293,25 +297,32 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
             for (int j = 0; j < 64; ++j)
               if (tb + j >= len) r[j] = 0.f;
           }
+          // (uniform branch on the row format so that each path carries exactly one conversion per pair)
+          auto pack_and_stage = [&](auto f16_tag) {
+            constexpr bool kF16 = decltype(f16_tag)::value;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            uint32_t pk[4];
+            for (int g = 0; g < 8; ++g) {
+              uint32_t pk[4];
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-              const int j = g * 8 + 2 * hh;
-              __nv_bfloat162 pr = __floats2bfloat162_rn(r[j], r[j + 1]);
-              pk[hh] = *reinterpret_cast<uint32_t*>(&pr);
-              if (p.stats) {
-                const float2 f = __bfloat1622float2(pr);
-                st_s += f.x + f.y;
-                st_ss = fmaf(f.x, f.x, fmaf(f.y, f.y, st_ss));
+              for (int hh = 0; hh < 4; ++hh) {
+                const int j = g * 8 + 2 * hh;
+                pk[hh] = kF16 ? pack_f16x2(r[j], r[j + 1]) : pack_bf16x2(r[j], r[j + 1]);
+                if (!kF16 && p.stats) {
+                  const float2 f = unpack_bf16x2(pk[hh]);
+                  st_s += f.x + f.y;
+                  st_ss = fmaf(f.x, f.x, fmaf(f.y, f.y, st_ss));
+                }
               }
+              // SWIZZLE_128B: 16-byte chunk g of row `lane` lives at chunk (g ^ (row & 7))
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((g ^ (lane & 7)) << 4)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                           : "memory");
             }
-            // SWIZZLE_128B: 16-byte chunk g of row `lane` lives at chunk (g ^ (row & 7))
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((g ^ (lane & 7)) << 4)),
-                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                         : "memory");
-          }
+          };
+          if (p.f16)
+            pack_and_stage(std::true_type{});
+          else
+            pack_and_stage(std::false_type{});
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -341,7 +352,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st, float* stats) {
+                        cudaStream_t st, float* stats, int f16) {
   if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
   pw3::Params p;
   memset(&p, 0, sizeof(p));
@@ -367,6 +378,8 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   p.num_tiles = p.m_tiles * p.n_tiles * B;
   p.shift = shift; p.lens = lens; p.out_pitch = out_pitch; p.relu = relu;
   p.stats = stats;
+  p.f16 = f16;
+  p.rev = next_walk_reversed();
   p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
   static int num_sms = 0;
   if (num_sms == 0) {

@@ -141,5 +141,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+// same with a runtime operand format: f16 != 0 selects IEEE fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int f16) {
+  return umma_idesc_bf16(M, N, a_mn_major, b_mn_major) & (f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
+}
+
 }  // namespace ptx
 }  // namespace ts

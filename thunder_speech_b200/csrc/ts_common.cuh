@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -18,6 +19,13 @@ int option_pw_big();  // 1: bf16-row GEMMs with Cout > 128 use the persistent 25
 int option_dw_tma();  // 1: pre-masked stride-1 depthwise convs use the TMA Toeplitz kernel (dwmma2.cu)
 int option_dw_mma();  // 1: stride-1 depthwise convs run on the tensor cores (dwmma.cu), 0: SIMT kernels only
 int option_pw_bn();   // experiment switch (see api.cu)
+int option_serpentine();  // 1: consecutive launches walk the utterances in alternating directions (L2 reuse)
+int option_dbg();     // scratch knob for experiments
+// L2 reuse between consecutive layers: the two streaming kernels (Toeplitz conv, pair GEMM) each move 2-4x the 126 MB L2
+// per launch, so when a kernel ends only the LAST ~60-100 MB it wrote are still resident.  Every launch of those kernels
+// therefore walks the utterances in the direction opposite to its predecessor's -- it starts on what is still in L2.
+// Pure scheduling hint (results are order independent); returns 0 / 1 alternately, always 0 with option serpentine = 0.
+int next_walk_reversed();
 
 #define TS_REQUIRE(cond, code, ...)            \
   do {                                         \
@@ -90,6 +98,35 @@ __device__ __forceinline__ void se_pool_add(unsigned long long* slot, float part
   atomicAdd(slot, static_cast<unsigned long long>(__float2ll_rn(partial * kSePoolScale)));
 }
 __device__ __forceinline__ float se_pool_value(long long fixed) { return static_cast<float>(static_cast<double>(fixed) * (1.0 / 4294967296.0)); }
+
+// ---- 16-bit row formats ------------------------------------------------------------------------
+// Activation rows are bf16 (default) or IEEE fp16 ("half rows": 11-bit mantissa, the mode that holds the 2e-2 logit
+// parity on the 15x5-deep networks; same bytes, same tcgen05 kind::f16 rate).  fp16 conversions SATURATE to +-65504
+// instead of producing inf, so an out-of-range activation degrades gracefully.  `f16` is kernel-uniform.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t w, bool f16) { return f16 ? unpack_f16x2(w) : unpack_bf16x2(w); }
+__device__ __forceinline__ float unpack16(uint16_t h, bool f16) {
+  return f16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+}
+__device__ __forceinline__ uint16_t pack16(float v, bool f16) { return (uint16_t)(pack16x2(v, 0.f, f16) & 0xFFFFu); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -61,19 +61,21 @@ def _bn_fold(bn: nn.BatchNorm1d) -> Tuple[Tensor, Tensor]:
     return scale, shift
 
 
-def _fold_pw(conv: nn.Conv1d, bn: nn.BatchNorm1d) -> Tuple[Tensor, Tensor]:
+def _fold_pw(conv: nn.Conv1d, bn: nn.BatchNorm1d, dtype: torch.dtype = torch.bfloat16) -> Tuple[Tensor, Tensor]:
     scale, shift = _bn_fold(bn)
     w = conv.weight.detach().float()[:, :, 0] * scale[:, None]
     if conv.bias is not None:
         shift = shift + conv.bias.detach().float() * scale
-    return w.to(torch.bfloat16).contiguous(), shift.contiguous()
+    if dtype == torch.float16:   # saturate like the kernels do (a folded weight beyond 65504 is pathological anyway)
+        w = w.clamp(-65504.0, 65504.0)
+    return w.to(dtype).contiguous(), shift.contiguous()
 
 
 def params_key(module: nn.Module):
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
-def build_block_plan(block: nn.Module) -> BlockPlan:
+def build_block_plan(block: nn.Module, dtype: torch.dtype = torch.bfloat16) -> BlockPlan:
     """Reads a block laid out like the reference (``mconv`` = [dw, pw, BN, (ReLU, Dropout)]*, optional SE,
     ``res`` = [conv1x1, BN]) and folds it into a plan.  Non-separable convs are supported for kernel_size 1
     (the only non-separable layer of the models, quartznet/blocks.py:399-407)."""
@@ -97,7 +99,7 @@ def build_block_plan(block: nn.Module) -> BlockPlan:
                     "non-separable convolutions are implemented for kernel_size=1, stride=1 only "
                     f"(got k={conv.kernel_size[0]}, s={conv.stride[0]}); the Quartznet/Citrinet models use "
                     "separable blocks everywhere else")
-            pw_w, shift = _fold_pw(conv, inner)
+            pw_w, shift = _fold_pw(conv, inner, dtype)
             if dwl is not None:
                 dw_w = dwl.conv.weight.detach().float()[:, 0, :].contiguous()
                 plan.subs.append(SubPlan(dw_w, dwl.kernel_size, dwl.stride, dwl.dilation, dwl.padding, pw_w, shift))
@@ -111,7 +113,7 @@ def build_block_plan(block: nn.Module) -> BlockPlan:
     if block.res is not None:
         rlayers = list(block.res.children())
         rconv, rbn = rlayers[0], rlayers[1].layer[0]
-        plan.res_w, plan.res_shift = _fold_pw(rconv.conv, rbn)
+        plan.res_w, plan.res_shift = _fold_pw(rconv.conv, rbn, dtype)
         plan.res_stride = rconv.stride
         if plan.res_stride > 1:
             plan.ones = torch.ones((rconv.conv.in_channels, 1), device=plan.res_w.device, dtype=torch.float32)
@@ -179,11 +181,16 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
 class PlannedBlock(nn.Module):
     """Mixin-style base of ``QuartznetBlock`` / ``CitrinetBlock``: lazy plan + the three ways to run it."""
 
-    def _plan(self) -> BlockPlan:
-        key = params_key(self)
+    def _plan(self, dtype: Optional[torch.dtype] = None) -> BlockPlan:
+        """Folded operands in the row format ``dtype`` (None = the package default precision)."""
+        if dtype is None:
+            from . import row_dtype
+
+            dtype = row_dtype()
+        key = (params_key(self), dtype)
         cached = getattr(self, "_plan_cache", None)
         if cached is None or cached[0] != key:
-            cached = (key, build_block_plan(self))
+            cached = (key, build_block_plan(self, dtype))
             object.__setattr__(self, "_plan_cache", cached)
         return cached[1]
 
@@ -197,7 +204,7 @@ class PlannedBlock(nn.Module):
     def forward_rows(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool):
         self._check_eval()
         with torch.no_grad():
-            return run_block(self._plan(), x, T, lens, zero_tail)
+            return run_block(self._plan(x.dtype), x, T, lens, zero_tail)
 
     def out_lengths(self, lengths: Tensor) -> Tensor:
         """Lengths after the main branch, computed with the reference's own formula on the caller's tensor
@@ -211,7 +218,9 @@ class PlannedBlock(nn.Module):
         """Drop-in ``(x[B,C,T], lengths[B]) -> (y[B,C',T'] f32, lengths')``."""
         self._check_eval()
         with torch.no_grad():
+            from . import row_dtype
+
             l32 = ops.lengths_i32(lengths)
-            rows = ops.pack_rows(x, l32)
-            y, T_out, _ = run_block(self._plan(), rows, x.shape[-1], l32, False)
+            rows = ops.pack_rows(x, l32, row_dtype() == torch.float16)
+            y, T_out, _ = run_block(self._plan(rows.dtype), rows, x.shape[-1], l32, False)
             return ops.unpack_rows(y, T_out), self.out_lengths(lengths)

@@ -46,18 +46,78 @@ class CTCModule(nn.Module):
 
         self.validation_cer = CharErrorRate()
         self.validation_wer = WordErrorRate()
+        self.precision: Optional[str] = None    # None = the package default (thunder_speech_b200.get_default_precision())
         self._dec_cache = None
         self._graphs: Dict[tuple, "_PredictGraph"] = {}
         self._pipes: Dict[tuple, "_StreamPipe"] = {}
+        self._graph_weights = None      # flat list of the tensors the captured graphs bake in (built lazily)
+        self._graph_fingerprint = None
+
+    # -- row format of the inference path ---------------------------------------------------------
+    def set_precision(self, precision: Optional[str]) -> "CTCModule":
+        """``"bf16"`` / ``"fp16"`` activation rows and GEMM operands for forward / predict (None = package default); see
+        ``thunder_speech_b200.set_default_precision``.  Captured graphs are per precision."""
+        from . import row_dtype
+
+        row_dtype(precision)     # validates
+        self.precision = precision
+        return self
+
+    def _row_dtype(self) -> torch.dtype:
+        from . import row_dtype
+
+        return row_dtype(self.precision)
+
+    # -- captured graphs are only valid for the weights they were captured with ----------------
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name in ("encoder", "decoder", "audio_transform") and "_graphs" in self.__dict__:
+            self.invalidate_graphs()
+
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .half(): parameters move, graphs die
+        out = super()._apply(fn, *args, **kwargs)
+        if "_graphs" in self.__dict__:
+            self.invalidate_graphs()
+        return out
+
+    def invalidate_graphs(self) -> None:
+        """Drop every captured inference graph and serving pipeline (they are rebuilt on the next graphed call).  Called
+        automatically when a weight / buffer of the encoder, decoder or front-end changes in place (``load_state_dict``,
+        an optimizer step, ``CTCTrainStep``), moves (``.to()``), or a sub-module is replaced; call it yourself after
+        replacing an individual ``nn.Parameter`` object deep inside a block."""
+        self._graphs.clear()
+        self._pipes.clear()
+        self._graph_weights = None
+        self._graph_fingerprint = None
+
+    def _weights_fingerprint(self) -> tuple:
+        """``(data_ptr, _version)`` of every parameter and buffer a captured forward reads (folded plans and the decoder
+        operands are derived from them at capture time, so the graph bakes in tensors that die when these change)."""
+        if self._graph_weights is None:
+            mods = [self.encoder, self.decoder, self.audio_transform]
+            self._graph_weights = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        return tuple((t.data_ptr(), t._version) for t in self._graph_weights)
+
+    def _check_graphs_current(self) -> None:
+        fp = self._weights_fingerprint()
+        if fp != self._graph_fingerprint:
+            if self._graph_fingerprint is not None:
+                self._graphs.clear()
+                self._pipes.clear()
+            self._graph_fingerprint = fp
 
     # -- decoder parameters as GEMM operands ----------------------------------------------------
     def _decoder_operands(self) -> Tuple[Tensor, Tensor]:
         dec = self.decoder
         if not isinstance(dec, nn.Conv1d) or dec.kernel_size[0] != 1:
             raise NotImplementedError("only conv1d_decoder (1x1 Conv1d with bias) is implemented")
-        key = (dec.weight.data_ptr(), dec.weight._version, dec.bias.data_ptr(), dec.bias._version)
+        dt = self._row_dtype()
+        key = (dec.weight.data_ptr(), dec.weight._version, dec.bias.data_ptr(), dec.bias._version, dt)
         if self._dec_cache is None or self._dec_cache[0] != key:
-            w = dec.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
+            w = dec.weight.detach()[:, :, 0].float()
+            if dt == torch.float16:
+                w = w.clamp(-65504.0, 65504.0)
+            w = w.to(dt).contiguous()
             b = dec.bias.detach().float().contiguous()
             self._dec_cache = (key, w, b)
         return self._dec_cache[1], self._dec_cache[2]
@@ -67,7 +127,8 @@ class CTCModule(nn.Module):
         N = x.shape[-1]
         hop = self.audio_transform[1].hop_length
         F = 1 + N // hop
-        feats, feat_len = self.audio_transform.features(x, lengths, bf16_pitch=ops.row_pitch(F))
+        feats, feat_len = self.audio_transform.features(x, lengths, bf16_pitch=ops.row_pitch(F),
+                                                        f16=self._row_dtype() == torch.float16)
         l32 = feat_len.to(torch.int32)
         rows, T, l32 = self.encoder.forward_rows(feats, F, l32)
         w, b = self._decoder_operands()
@@ -103,7 +164,8 @@ class CTCModule(nn.Module):
         input shape into a CUDA graph and replayed (launch-bound otherwise at small batch).  By default the audio is
         copied into the graph's own input buffer; ``in_place=True`` declares ``x`` a persistent device buffer owned by the
         caller (a DMA staging buffer): the graph captured for it reads ``x`` where it lies, one graph per such buffer."""
-        key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None)
+        self._check_graphs_current()    # stale weights must never be replayed (train / load_state_dict in between)
+        key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None, self._row_dtype())
         g = self._graphs.get(key)
         if g is None:
             if in_place:    # a caller that passes a fresh tensor every time must not accumulate graphs (and their memory pools)

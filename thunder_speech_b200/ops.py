@@ -54,16 +54,32 @@ def _ptr(t: Tensor) -> int:
     return t.data_ptr()
 
 
+#: the two 16-bit row formats: bf16 (default) and IEEE fp16 ("half rows": 11-bit mantissa, saturating conversions)
+ROW_DTYPES = (torch.bfloat16, torch.float16)
+
+
+def _row_tag(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return _lib.TS_BF16
+    if t.dtype == torch.float16:
+        return _lib.TS_F16
+    raise TypeError(f"activation rows must be bfloat16 or float16, got {t.dtype}")
+
+
+def _f16_flag(t: Tensor) -> int:
+    return _lib.TS_ROWS_F16 if _row_tag(t) == _lib.TS_F16 else 0
+
+
 # ------------------------------------------------------------------------------------------- features
 @torch.library.custom_op(f"{NS}::filterbank", mutates_args=())
 def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Tensor, mel_start: Tensor,
                mel_count: Tensor, mel_off: Tensor, mel_w: Tensor, hop: int, preemph: float, win_lo: int,
-               win_hi: int, div_guard: float, out_bf16_pitch: int) -> Tuple[Tensor, Tensor]:
+               win_hi: int, div_guard: float, out_bf16_pitch: int, out_f16: bool = False) -> Tuple[Tensor, Tensor]:
     """Eval-mode ``FilterbankFeatures`` (src/thunder/quartznet/transform.py:258-321).
 
     ``out_bf16_pitch == 0``: returns ``(features[B,nfilt,F] f32, feature_lengths[B] i64)`` exactly like the
-    reference.  ``out_bf16_pitch > 0``: features are emitted as bf16 padded rows ``[B,nfilt,pitch]`` for the
-    encoder kernels."""
+    reference.  ``out_bf16_pitch > 0``: features are emitted as 16-bit padded rows ``[B,nfilt,pitch]`` for the
+    encoder kernels (bf16, or fp16 with ``out_f16``)."""
     _need_cuda(audio, lengths, window_full, twiddle, mel_start, mel_count, mel_off, mel_w)
     if audio.dim() != 2:
         raise ValueError("audio must be [batch, time]")
@@ -80,8 +96,9 @@ def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Ten
                            mel_w.numel(), _ptr(logmel), _stream()), "ts_logmel")
     seq = torch.empty((B,), device=audio.device, dtype=torch.int64)
     if out_bf16_pitch > 0:
-        out = torch.empty((B, nfilt, out_bf16_pitch), device=audio.device, dtype=torch.bfloat16)
-        dt, pitch = _lib.TS_BF16, out_bf16_pitch
+        out = torch.empty((B, nfilt, out_bf16_pitch), device=audio.device,
+                          dtype=torch.float16 if out_f16 else torch.bfloat16)
+        dt, pitch = (_lib.TS_F16 if out_f16 else _lib.TS_BF16), out_bf16_pitch
     else:
         out = torch.empty((B, nfilt, F), device=audio.device, dtype=torch.float32)
         dt, pitch = _lib.TS_F32, F
@@ -92,12 +109,12 @@ def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Ten
 
 @filterbank.register_fake
 def _(audio, lengths, window_full, twiddle, mel_start, mel_count, mel_off, mel_w, hop, preemph, win_lo, win_hi,
-      div_guard, out_bf16_pitch):
+      div_guard, out_bf16_pitch, out_f16=False):
     B, N = audio.shape
     nfilt = mel_start.numel()
     F = 1 + N // hop
     if out_bf16_pitch > 0:
-        out = audio.new_empty((B, nfilt, out_bf16_pitch), dtype=torch.bfloat16)
+        out = audio.new_empty((B, nfilt, out_bf16_pitch), dtype=torch.float16 if out_f16 else torch.bfloat16)
     else:
         out = audio.new_empty((B, nfilt, F), dtype=torch.float32)
     return out, audio.new_empty((B,), dtype=torch.int64)
@@ -110,25 +127,26 @@ def row_pitch(T: int) -> int:
 
 
 @torch.library.custom_op(f"{NS}::pack_rows", mutates_args=())
-def pack_rows(x: Tensor, lens: Optional[Tensor] = None) -> Tensor:
-    """``[B, C, T]`` (f32 / bf16, contiguous) -> bf16 padded rows ``[B, C, row_pitch(T)]``; pad frames and, when
-    ``lens`` (i32 ``[B]``) is given, frames ``t >= lens[b]`` are zero (``MaskedConv1d.mask_fill``)."""
+def pack_rows(x: Tensor, lens: Optional[Tensor] = None, f16: bool = False) -> Tensor:
+    """``[B, C, T]`` (f32 / bf16 / fp16, contiguous) -> 16-bit padded rows ``[B, C, row_pitch(T)]`` (bf16, or fp16 with
+    ``f16``); pad frames and, when ``lens`` (i32 ``[B]``) is given, frames ``t >= lens[b]`` are zero
+    (``MaskedConv1d.mask_fill``)."""
     _need_cuda(x)
-    if x.dtype not in (torch.float32, torch.bfloat16):
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         x = x.float()
     x = x.contiguous()
     B, C, T = x.shape
-    out = torch.empty((B, C, row_pitch(T)), device=x.device, dtype=torch.bfloat16)
-    dt = _lib.TS_F32 if x.dtype == torch.float32 else _lib.TS_BF16
+    out = torch.empty((B, C, row_pitch(T)), device=x.device, dtype=torch.float16 if f16 else torch.bfloat16)
+    dt = _lib.TS_F32 if x.dtype == torch.float32 else _row_tag(x)
     _lib.check(_lib.lib().ts_pack_rows(_ptr(x), dt, B, C, T, _ptr(lens) if lens is not None else None, _ptr(out),
-                                       out.shape[2], _stream()), "ts_pack_rows")
+                                       _row_tag(out), out.shape[2], _stream()), "ts_pack_rows")
     return out
 
 
 @pack_rows.register_fake
-def _(x, lens=None):
+def _(x, lens=None, f16=False):
     B, C, T = x.shape
-    return x.new_empty((B, C, row_pitch(T)), dtype=torch.bfloat16)
+    return x.new_empty((B, C, row_pitch(T)), dtype=torch.float16 if f16 else torch.bfloat16)
 
 
 @torch.library.custom_op(f"{NS}::unpack_rows", mutates_args=())
@@ -137,7 +155,7 @@ def unpack_rows(x: Tensor, T: int) -> Tensor:
     _need_cuda(x)
     B, C, pitch = x.shape
     out = torch.empty((B, C, T), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ts_unpack_rows(_ptr(x), pitch, B, C, T, _ptr(out), _stream()), "ts_unpack_rows")
+    _lib.check(_lib.lib().ts_unpack_rows(_ptr(x), _row_tag(x), pitch, B, C, T, _ptr(out), _stream()), "ts_unpack_rows")
     return out
 
 
@@ -162,11 +180,12 @@ def dw_conv(x: Tensor, T_in: int, weight: Tensor, stride: int, dilation: int, pa
     B, C, pitch = x.shape
     K = weight.shape[1]
     T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
-    out = torch.empty((B, C, row_pitch(max(T_out, 1))), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((B, C, row_pitch(max(T_out, 1))), device=x.device, dtype=x.dtype)
     with _timed("dw_conv", bytes=2 * B * C * (T_in + T_out), flops=2 * B * C * T_out * K, K=K, C=C, T=T_out):
         _lib.check(_lib.lib().ts_dw_conv(_ptr(x), B, C, T_in, pitch, _ptr(weight), K, stride, dilation, padding,
                                          _ptr(lens) if lens is not None else None,
-                                         _lib.TS_DW_INPUT_PREMASKED if premasked else 0, _ptr(out), out.shape[2],
+                                         (_lib.TS_DW_INPUT_PREMASKED if premasked else 0) | _f16_flag(x), _ptr(out),
+                                         out.shape[2],
                                          _stream()), "ts_dw_conv")
     return out
 
@@ -196,8 +215,11 @@ def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], 
         out = torch.empty((B, Cout, T), device=x0.device, dtype=torch.float32)
         dt, pitch = _lib.TS_F32, T
     else:
-        out = torch.empty((B, Cout, row_pitch(T)), device=x0.device, dtype=torch.bfloat16)
-        dt, pitch = _lib.TS_BF16, out.shape[2]
+        out = torch.empty((B, Cout, row_pitch(T)), device=x0.device, dtype=x0.dtype)
+        dt, pitch = _row_tag(x0), out.shape[2]
+    for t in (w0, w1, x1, y1):
+        if t is not None and t.dtype != x0.dtype:
+            raise TypeError(f"pw_gemm: operands must share the row format of x0 ({x0.dtype}), got {t.dtype}")
     cin1 = x1.shape[1] if x1 is not None else 0
     p1 = x1.shape[2] if x1 is not None else 0
 
@@ -208,7 +230,8 @@ def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], 
     nbytes = 2 * B * T * kin + 2 * Cout * kin + (4 if out_f32 else 2) * B * T * Cout + (2 * B * T * Cout if y1 is not None else 0)
     with _timed("pw_gemm", bytes=nbytes, flops=2 * B * T * kin * Cout, K=kin, C=Cout, T=T):
         _lib.check(_lib.lib().ts_pw_gemm(_ptr(w0), _ptr(x0), cin0, p0, P(w1), P(x1), cin1, p1, B, Cout, T, P(shift),
-                                         P(lens), _ptr(out), dt, pitch, int(relu), P(pool), P(se_scale), P(y1),
+                                         P(lens), _ptr(out), dt, pitch,
+                                         (_lib.TS_PW_RELU if relu else 0) | _f16_flag(x0), P(pool), P(se_scale), P(y1),
                                          y1.shape[2] if y1 is not None else 0, _stream()), "ts_pw_gemm")
     return out
 
@@ -278,7 +301,8 @@ def se_apply(y1: Tensor, gate: Tensor, lens: Optional[Tensor], relu: bool) -> Te
     B, C, pitch = y1.shape
     out = torch.empty_like(y1)
     _lib.check(_lib.lib().ts_se_apply(_ptr(y1), _ptr(gate), B, C, pitch, _ptr(lens) if lens is not None else None,
-                                      int(relu), _ptr(out), _stream()), "ts_se_apply")
+                                      (_lib.TS_PW_RELU if relu else 0) | _f16_flag(y1), _ptr(out), _stream()),
+               "ts_se_apply")
     return out
 
 
@@ -309,7 +333,7 @@ def gather_rows(x: Tensor, T_in: int, stride: int, lens: Optional[Tensor]) -> Te
     _need_cuda(x)
     B, C, pitch = x.shape
     T_out = (T_in - 1) // stride + 1
-    out = torch.empty((B, C, row_pitch(T_out)), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((B, C, row_pitch(T_out)), device=x.device, dtype=x.dtype)
     _lib.check(_lib.lib().ts_gather_rows(_ptr(x), B, C, T_in, pitch, stride, _ptr(lens) if lens is not None else None,
                                          _ptr(out), out.shape[2], _stream()), "ts_gather_rows")
     return out

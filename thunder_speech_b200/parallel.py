@@ -37,6 +37,38 @@ def sharded_predict(predict: Callable[[torch.Tensor], List[str]], audio: torch.T
     return out
 
 
+def sharded_predict_stream(module, batches, group=None, depth: int = 3, presharded: bool = False) -> List[List[str]]:
+    """Strong-scaling serving loop (BASELINE configs 3 / 4: "batch-sharded at 1/2/4/8"): every rank runs
+    ``module.predict_stream`` over ITS contiguous slice of each host batch ``[B, N]`` (``presharded=True``: the iterable
+    already yields this rank's slice) -- H2D, graph replay, D2H and detokenisation of its own utterances, no data-path
+    collective -- and the transcripts of all batches are gathered ONCE at the end of the stream (one
+    ``all_gather_object``: the only exchange of the inference path).  Returns, on every rank, one list of ``B``
+    transcripts per batch in the original utterance order."""
+    on = dist.is_available() and dist.is_initialized()
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
+
+    def local(it):
+        for xb in it:
+            if presharded or world == 1:
+                yield xb
+            else:
+                lo, hi = shard_bounds(xb.shape[0], world, rank)
+                yield xb[lo:hi]
+
+    mine = [texts for texts in module.predict_stream(local(batches), depth=depth)]
+    if world == 1:
+        return mine
+    parts: List[Sequence[Sequence[str]]] = [None] * world  # type: ignore[list-item]
+    dist.all_gather_object(parts, mine, group=group)
+    out: List[List[str]] = []
+    for i in range(len(mine)):
+        row: List[str] = []
+        for p in parts:
+            row.extend(p[i])
+        out.append(row)
+    return out
+
+
 def flat_grad_views(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
     """Allocates ONE flat fp32 buffer holding every parameter's gradient and points each ``param.grad`` at its slice, so
     that data-parallel training (BASELINE config 5) averages gradients with a single in-place collective and no packing."""

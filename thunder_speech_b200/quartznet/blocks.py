@@ -42,8 +42,10 @@ class MaskedConv1d(nn.Module):
         conv = self.conv
         with torch.no_grad():
             l32 = ops.lengths_i32(lengths) if self.use_mask else None
+            from .. import row_dtype
+
             T = x.shape[-1]
-            rows = ops.pack_rows(x, l32)
+            rows = ops.pack_rows(x, l32, row_dtype() == torch.float16)
             if conv.groups == conv.in_channels and conv.out_channels == conv.in_channels and conv.groups > 1:
                 w = conv.weight.detach().float()[:, 0, :].contiguous()
                 # the kernel masks its output for the following pointwise conv; stand-alone semantics are
@@ -54,7 +56,7 @@ class MaskedConv1d(nn.Module):
                 if conv.bias is not None:
                     out = out + conv.bias.detach().float()[None, :, None]
             elif self.kernel_size == 1 and self.stride == 1 and conv.groups == 1 and self.padding == 0:
-                w = conv.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous()
+                w = conv.weight.detach()[:, :, 0].to(rows.dtype).contiguous()
                 bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
                 out = ops.pw_gemm(w, rows, None, None, T, bias, None, True, False, None, None, None)
             else:
@@ -157,8 +159,10 @@ class EncoderBase(MultiSequential):
 
     def forward(self, x: Tensor, lengths: Tensor) -> Tuple[Tensor, Tensor]:
         with torch.no_grad():
+            from .. import row_dtype
+
             l32 = ops.lengths_i32(lengths)
-            rows = ops.pack_rows(x, l32)
+            rows = ops.pack_rows(x, l32, row_dtype() == torch.float16)
             y, T_out, _ = self.forward_rows(rows, x.shape[-1], l32)
             return ops.unpack_rows(y, T_out), self.out_lengths(lengths)
 

@@ -177,8 +177,9 @@ class _FusedFilterbank(nn.Sequential):
         self._tables = (key, t)
         return t
 
-    def features(self, audio: Tensor, lengths: Tensor, bf16_pitch: int = 0) -> Tuple[Tensor, Tensor]:
-        """Run the fused front-end.  ``bf16_pitch > 0`` emits bf16 padded rows for the encoder kernels."""
+    def features(self, audio: Tensor, lengths: Tensor, bf16_pitch: int = 0, f16: bool = False) -> Tuple[Tensor, Tensor]:
+        """Run the fused front-end.  ``bf16_pitch > 0`` emits 16-bit padded rows for the encoder kernels (bf16, or fp16
+        with ``f16``)."""
         from .. import ops  # registers torch.ops.thunder_b200.*
 
         dither: DitherAudio = self[0].layer[0]
@@ -192,7 +193,7 @@ class _FusedFilterbank(nn.Sequential):
             feats, feat_len = torch.ops.thunder_b200.filterbank(
                 audio, lengths, t["window_full"], t["twiddle"], t["mel_start"], t["mel_count"], t["mel_off"],
                 t["mel_w"], ps.hop_length, float(pre.preemph), t["win_lo"], t["win_hi"], float(norm.div_guard),
-                int(bf16_pitch))
+                int(bf16_pitch), bool(f16))
             if self.training and len(self) > 4:   # SpecCutout / SpecAugment: in place on the fresh feature tensor
                 from .spec_augment import apply_rects
 

@@ -58,8 +58,12 @@ class ModelWorkload:
     dtype = "bf16"
 
     def __init__(self, name, B, N, nfilt, dev, rank):
+        from . import get_default_precision
+
         self.name, self.B, self.N, self.dev = name, B, N, dev
         self.model = build_model(name, dev)
+        self.precision = self.model.precision or get_default_precision()
+        self.dtype = "f16" if self.precision == "fp16" else "bf16"
         host = torch.from_numpy(synth.audio(B, N, 1234 + rank, "noise"))
         self.host_audio = host.pin_memory()
         self.audio = [(self.host_audio.to(dev) * (1.0 + 0.01 * i)).contiguous() for i in range(self.NBUF)]
@@ -88,10 +92,11 @@ class ModelWorkload:
         """The serving-loop user call: ``predict_stream`` over ``steps`` pinned host batches -- every step still
         copies its own audio host->device and its token ids device->host inside the timed region; the copies
         overlap the neighbouring steps' compute."""
-        n = 0
-        for texts in self.model.predict_stream(self.host_audio for _ in range(steps)):
-            n += len(texts)
-        return n
+        from .parallel import sharded_predict_stream
+
+        # every rank streams ITS shard of each batch; the transcripts of all ranks are gathered at the end of the stream
+        out = sharded_predict_stream(self.model, (self.host_audio for _ in range(steps)), presharded=True)
+        return sum(len(t) for t in out)
 
     def roofline(self, steps):
         """Eager pass with CUDA events around every kernel launch; reports the kernel class with the largest

@@ -808,11 +808,32 @@ class CTCTrainStep:
 
     All gradients live in ONE flat fp32 buffer (``param.grad`` are views): the all-reduce is a single in-place collective.
     With ``use_graph`` the whole forward + loss + backward (~890 launches for QuartzNet 15x5) is captured in a CUDA graph
-    per input shape and replayed; inputs are copied into the graph's static buffers."""
+    per input shape and replayed; inputs are copied into the graph's static buffers.  Graphs need FIXED OR BUCKETED shapes:
+    every new ``(audio.shape, y.shape)`` costs two warm-up passes plus a capture and holds its own memory pool, so at most
+    ``MAX_GRAPHS`` are kept (least recently used evicted) -- pad audio / targets to a few bucket lengths before calling, or
+    pass ``use_graph=False`` for free-form shapes.
+
+    Not implemented, and refused loudly instead of silently differing from the reference: dropout ``p > 0`` in train mode
+    (the reference applies it after every ReLU, quartznet/blocks.py:225-228), BatchNorm modules switched to ``eval()``
+    inside a training step (the fine-tuning callback's ``train_bn=False``) and frozen (``requires_grad=False``)
+    parameters."""
+
+    MAX_GRAPHS = 8
 
     def __init__(self, module, lr: float = 3e-4, blank_idx: Optional[int] = None,
                  optimizer: Optional[torch.optim.Optimizer] = None, use_graph: bool = True):
         self.m = module
+        for name, mod in list(module.encoder.named_modules()) + list(module.decoder.named_modules()):
+            if isinstance(mod, nn.Dropout) and mod.p > 0:
+                raise NotImplementedError(
+                    f"CTCTrainStep: dropout p={mod.p} at encoder.{name} is not implemented by the training kernels (the "
+                    "reference applies it after every ReLU in train mode); build the encoder with dropout=0.0")
+        frozen = [n for n, p_ in list(module.encoder.named_parameters()) + list(module.decoder.named_parameters())
+                  if not p_.requires_grad]
+        if frozen:
+            raise NotImplementedError(
+                f"CTCTrainStep: {len(frozen)} frozen parameters (requires_grad=False, first: {frozen[0]}): the fused "
+                "optimizer updates every encoder / decoder parameter; partial fine-tuning is not implemented")
         self.enc = EncoderTrainer(module.encoder)
         self.enc.extra_entries.append(("pw", module.decoder.weight))
         self.params = [p for p in list(module.encoder.parameters()) + list(module.decoder.parameters())]
@@ -880,6 +901,7 @@ class CTCTrainStep:
     def loss_and_grads(self, audio: Tensor, lengths: Tensor, y: Tensor, y_lengths: Tensor) -> Tensor:
         """Mean CTC loss (device scalar); parameter gradients are left in ``param.grad``."""
         if not self.use_graph:
+            self._check_bn_mode()
             loss = self._forward_backward(audio, lengths, y, y_lengths)
             self._bump_buffer_versions()
             return loss
@@ -890,10 +912,14 @@ class CTCTrainStep:
         if ptrs != getattr(self, "_captured_ptrs", ptrs):
             self._graphs.clear()          # parameters were re-allocated: the captured graphs point at stale storage
         self._captured_ptrs = ptrs
+        self._check_bn_mode()
         key = (tuple(audio.shape), tuple(y.shape))
-        g = self._graphs.get(key)
+        g = self._graphs.pop(key, None)
         if g is None:
-            g = self._graphs[key] = self._capture(audio, lengths, y, y_lengths)
+            while len(self._graphs) >= self.MAX_GRAPHS:      # least recently used first (dicts keep insertion order)
+                del self._graphs[next(iter(self._graphs))]
+            g = self._capture(audio, lengths, y, y_lengths)
+        self._graphs[key] = g                                # (re-)insert as most recently used
         g.audio.copy_(audio, non_blocking=True)
         g.lengths.copy_(lengths, non_blocking=True)
         g.y.copy_(y, non_blocking=True)
@@ -901,7 +927,14 @@ class CTCTrainStep:
         g.graph.replay()
         g.replays += 1
         self._bump_buffer_versions()
-        return g.loss
+        return g.loss.clone()     # the graph's static output is overwritten by the next replay
+
+    def _check_bn_mode(self) -> None:
+        for name, mod in self.m.encoder.named_modules():
+            if isinstance(mod, nn.BatchNorm1d) and not mod.training:
+                raise NotImplementedError(
+                    f"CTCTrainStep: BatchNorm encoder.{name} is in eval() mode; the training kernels always normalise with "
+                    "batch statistics and update the running ones (frozen-BN fine-tuning is not implemented)")
 
     def _bump_buffer_versions(self) -> None:
         """The kernels update BatchNorm running statistics through raw pointers; tell torch (caches keyed on `_version`)."""
