@@ -277,7 +277,7 @@ def measure(args, workload, world, rank, local_rank, dev, barrier, with_cpu_base
         B, global_batch = B_total, B_total * world
     assert B > 0, f"rank {rank} has no utterances: batch {B_total} over {world} ranks"
     N = secs * SAMPLE_RATE
-    wl = BW.make(workload, B, N, nfilt, dev, rank)
+    wl = BW.make(workload, B, N, nfilt, dev, rank, pcm16=args.pcm16)
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------
     for i in range(args.warmup):
@@ -345,7 +345,9 @@ def measure(args, workload, world, rank, local_rank, dev, barrier, with_cpu_base
             "config": {"workload": desc, "global_batch": global_batch, "per_gpu_batch": B, "seconds": secs,
                        "parallelism": f"batch-shard x{world}" + ("" if world == 1 else
                                                                    " (no data-path collective; transcripts gathered in e2e)"),
-                       "precision": getattr(wl, "precision", wl.dtype), "l2": wl.l2_note},
+                       "precision": getattr(wl, "precision", wl.dtype),
+                       "e2e_input": "int16 PCM from pinned host memory, scaled on the device (ts_pcm_ingest)" if args.pcm16
+                       else "float32 audio from pinned host memory", "l2": wl.l2_note},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof,
         }
@@ -412,6 +414,7 @@ def main():
                     help="strong (default): the configuration's batch is SHARDED over the GPUs (BASELINE configs 3 / 4: "
                          "256 -> 32 per GPU at 8); weak: every GPU runs the full per-GPU batch")
     ap.add_argument("--precision", default=None, choices=["bf16", "fp16"], help="row format of the inference path")
+    ap.add_argument("--pcm16", action="store_true", help="e2e leg feeds int16 PCM (half the host-to-device bytes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the Citrinet-1024 leg of the default line")
     ap.add_argument("--batch", type=int, default=None, help="override the configuration's batch (experiments only)")

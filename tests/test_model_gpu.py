@@ -211,6 +211,23 @@ def test_predict_stream_matches_predict(depth, nbatch):
     assert list(m.predict_stream(list(reversed(xs)), depth=depth)) == list(reversed(want))
 
 
+def test_predict_stream_int16_pcm():
+    """predict_stream on int16 PCM (what a wav file holds; half the H2D bytes) == predict on the same samples scaled by
+    1/32768 on the host like torchaudio.load; with remove_dc the per-utterance mean is subtracted like the reference's
+    AudioFileLoader (src/thunder/data/dataset.py:50-77)."""
+    m, _ = build_qn5x5()
+    rng = np.random.default_rng(3)
+    pcm = [torch.from_numpy((synth.audio(2, 9000, 60 + i, "tones") * 30000 + 700).round().clip(-32768, 32767).astype(np.int16))
+           for i in range(4)]
+    want = [m.predict((p.float() / 32768.0).cuda()) for p in pcm]
+    assert list(m.predict_stream([p.pin_memory() for p in pcm], depth=3)) == want
+    f = [p.float() / 32768.0 for p in pcm]
+    want_dc = [m.predict((x - x.mean(1, keepdim=True)).cuda()) for x in f]
+    assert list(m.predict_stream([p.pin_memory() for p in pcm], depth=2, remove_dc=True)) == want_dc
+    with pytest.raises(TypeError):
+        list(m.predict_stream([pcm[0].to(torch.int32)]))
+
+
 def test_to_torchscript_trace_roundtrip(tmp_path):
     """`CTCModule.to_torchscript` (trace over the thunder_b200 custom ops): bit-identical logits, save / load, another batch
     size of the same audio length (the reference exports through Lightning's to_torchscript, module.py:88 @jit.export)."""
@@ -227,7 +244,7 @@ def test_to_torchscript_trace_roundtrip(tmp_path):
     ts = m.to_torchscript(x, lens, file_path=path)
     out, ol = ts(x, lens)
     assert torch.equal(out, ref) and torch.equal(ol, rl)
-    kinds = {n.kind() for n in ts.graph.nodes()}
+    kinds = {n.kind() for n in ts.traced.graph.nodes()}
     assert {"thunder_b200::filterbank", "thunder_b200::dw_conv", "thunder_b200::pw_gemm"} <= kinds
     loaded = torch.jit.load(path)
     x3 = torch.from_numpy(synth.audio(3, 16000, 4, "tones")).cuda()
@@ -235,6 +252,10 @@ def test_to_torchscript_trace_roundtrip(tmp_path):
     o3, _ = loaded(x3, l3)
     r3, _ = m(x3, l3)
     assert torch.equal(o3, r3)
+    # the reference's second exported entry point (@torch.jit.export predict, src/thunder/module.py:88-100): strings out of
+    # TorchScript, before and after save / load, other batch size
+    assert ts.predict(x) == m.predict(x)
+    assert loaded.predict(x3) == m.predict(x3)
 
 
 def test_random_block_configurations_vs_oracle():

@@ -80,9 +80,9 @@ class FeaturesWorkload(_Base):
                 "algorithmic_bytes": alg, "avg_kernel_ms": ms, "traffic": None}
 
 
-def make(name, B, N, nfilt, dev, rank):
+def make(name, B, N, nfilt, dev, rank, pcm16: bool = False):
     if name == "features":
         return FeaturesWorkload(B, N, nfilt, dev, rank)
     from . import runner  # encoder workloads need the model runner
 
-    return runner.make_bench_workload(name, B, N, nfilt, dev, rank)
+    return runner.make_bench_workload(name, B, N, nfilt, dev, rank, pcm16)

@@ -23,7 +23,9 @@ static Option g_options[] = {
     {"dw_mma", {1}},          // stride-1 depthwise convs on the tensor cores
     {"pw_big", {1}},          // persistent 256-wide GEMM tiles for 16-bit outputs with Cout > 128
     {"dw_tma", {1}},          // TMA-fed Toeplitz kernel for pre-masked rows
+    {"dw_persist", {1}},      // persistent multi-channel Toeplitz CTAs (dwmma3.cu): 0 never, 1 heuristic (few tiles per channel), 2 always
     {"pw_bn", {0}},
+    {"pw_resident", {0}},     // pair GEMM keeps the weight rows of its m-tile in shared memory when K <= 512 (measured: -7 %, off)
     {"pdl", {3}},             // programmatic dependent launch: bit 0 inference kernels, bit 1 training kernels
     {"pw_pair", {2}},         // CTA-pair GEMM: 1 = only K >= 1024, 2 = every 16-bit-row GEMM with Cout > 128
     {"dw_base_offset", {0}},
@@ -39,9 +41,11 @@ static std::atomic<int>& opt(const char* name) {
 }
 int option_pdl() { return opt("pdl").load(std::memory_order_relaxed); }
 int option_pw_pair() { return opt("pw_pair").load(std::memory_order_relaxed); }
+int option_pw_resident() { return opt("pw_resident").load(std::memory_order_relaxed); }
 int option_pw_bn() { return opt("pw_bn").load(std::memory_order_relaxed); }
 int option_dw_pro() { return opt("dw_pro").load(std::memory_order_relaxed); }
 int option_dw_share_halo() { return opt("dw_share_halo").load(std::memory_order_relaxed); }
+int option_dw_persist() { return opt("dw_persist").load(std::memory_order_relaxed); }
 int option_dw_tma() { return opt("dw_tma").load(std::memory_order_relaxed); }
 int option_dw_base_offset() { return opt("dw_base_offset").load(std::memory_order_relaxed); }
 int option_dw_mma() { return opt("dw_mma").load(std::memory_order_relaxed); }

@@ -22,7 +22,9 @@ constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;   // tile of the CTA PAI
 constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 weight rows: 16 KB
 constexpr int B_BYTES = BK * (BN / 2) * 2;     // this CTA's half of the activation tile: 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGES = 6;
+constexpr int STAGES = 6;                      // streaming mode: 6 stages of (A rows + B half) = 32 KB
+constexpr int UNITS = 12;                      // 16 KB units next to the epilogue staging: resident A chunks + B-only stages
+constexpr int MAX_STAGES = 12;
 constexpr int ACC = 2;
 constexpr int EPI_WARPS = 8;
 constexpr int STG_BYTES = 32 * 128;
@@ -46,6 +48,9 @@ struct Params {
   const __nv_bfloat16* y1;
   int y1_pitch;
   int f16;            // operands and 16-bit output rows are IEEE fp16 instead of bf16
+  int res_kc;         // > 0: WEIGHT-STATIONARY mode -- this CTA's 128 weight rows x all res_kc k-chunks stay in shared
+                      // memory for the whole kernel (every pair owns ONE m-tile) and the ring streams activations only
+  int nst;            // ring stages (6 x 32 KB streaming, 12 - res_kc x 16 KB weight-stationary)
   int rev;            // walk the (utterance, frame-tile) space from the far end (see next_walk_reversed())
 };
 
@@ -128,17 +133,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;    // == UNITS * 16 KB: [resident A chunks | ring] then the staging tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
+  uint64_t* a_full = tmem_empty + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  const bool resident = p.res_kc > 0;
+  uint8_t* ring = smem + p.res_kc * A_BYTES;
+  const int ring_stage = resident ? B_BYTES : STAGE_BYTES;
+  const int nst = p.nst;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.kc0 + p.kc1;
   const uint32_t rank = cluster_ctarank();     // 0 = leader
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  // i-th tile of this pair -> (m-tile, frame tile, utterance).  Streaming: tiles are dealt round-robin.  Weight-stationary:
+  // pair p owns m-tile p % m_tiles and strides over the (frame tile, utterance) space with the pairs that share it.
+  const int nb_tiles = p.num_tiles / p.m_tiles;
+  const int pairs_per_mt = npairs / p.m_tiles;
+  auto tile_at = [&](int i, int& mt, int& nt, int& b) -> bool {
+    int rest;
+    if (resident) {
+      if (pair >= pairs_per_mt * p.m_tiles) return false;
+      rest = pair / p.m_tiles + i * pairs_per_mt;
+      if (rest >= nb_tiles) return false;
+      mt = pair % p.m_tiles;
+    } else {
+      const int tile = pair + i * npairs;
+      if (tile >= p.num_tiles) return false;
+      mt = tile % p.m_tiles;
+      rest = tile / p.m_tiles;
+    }
+    if (p.rev) rest = nb_tiles - 1 - rest;
+    nt = rest % p.n_tiles;
+    b = rest / p.n_tiles;
+    return true;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.a0);
@@ -150,10 +182,11 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 2);      // only the leader's copy is used: one arrival per CTA + both CTAs' bytes
       ptx::mbar_init(&empty_bar[s], 1);
     }
+    ptx::mbar_init(a_full, 2);
     for (int a = 0; a < ACC; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], 2 * EPI_WARPS * 32);   // leader's copy: epilogue threads of both CTAs
@@ -177,25 +210,35 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: runs ahead over this CTA's whole tile list =====
     uint32_t cnt = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += npairs) {
-      const int mt = tile % p.m_tiles, rest = p.rev ? p.num_tiles / p.m_tiles - 1 - tile / p.m_tiles : tile / p.m_tiles;
-      const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
+    int mt, nt, b;
+    if (resident && tile_at(0, mt, nt, b)) {   // the weights of this pair's m-tile: loaded ONCE, all k-chunks
+      const int m0 = mt * BM + 128 * (int)rank;
+      if (rank == 0)
+        ptx::mbar_arrive_expect_tx(a_full, 2 * p.res_kc * A_BYTES);
+      else
+        mbar_arrive_remote(a_full, 0);
+      for (int kc = 0; kc < num_k; ++kc) {
+        const bool seg1 = kc >= p.kc0;
+        tma2_load_2d(smem + kc * A_BYTES, seg1 ? &p.a1 : &p.a0, a_full, (seg1 ? kc - p.kc0 : kc) * BK, m0);
+      }
+    }
+    for (int i = 0; tile_at(i, mt, nt, b); ++i) {
       const int m0 = mt * BM + 128 * (int)rank;          // this CTA's 128 output channels
       const int t0 = nt * BN + (BN / 2) * (int)rank;     // this CTA's half of the frame tile
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
-        const int s = cnt % STAGES;
-        ptx::mbar_wait(&empty_bar[s], ((cnt / STAGES) & 1) ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
+        const int s = cnt % nst;
+        ptx::mbar_wait(&empty_bar[s], ((cnt / nst) & 1) ^ 1);
+        uint8_t* sa = ring + s * ring_stage;
+        uint8_t* sb = resident ? sa : sa + A_BYTES;
         if (rank == 0)
-          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * ring_stage);
         else
           mbar_arrive_remote(&full_bar[s], 0);
         const bool seg1 = kc >= p.kc0;
         const CUtensorMap* ma = seg1 ? &p.a1 : &p.a0;
         const CUtensorMap* mb = seg1 ? &p.b1 : &p.b0;
         const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
-        tma2_load_2d(sa, ma, &full_bar[s], k0, m0);                      // [128 rows x 64 k]
+        if (!resident) tma2_load_2d(sa, ma, &full_bar[s], k0, m0);       // [128 rows x 64 k]
 #pragma unroll
         for (int j = 0; j < BN / 128; ++j)
           tma2_load_3d(sb + j * (BK * 128), mb, &full_bar[s], t0 + 64 * j, k0, b);
@@ -204,17 +247,23 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ===== MMA issuer (leader CTA only) =====
     const uint32_t idesc = ptx::umma_idesc_16(256, BN, 0, 1, p.f16);
-    uint32_t cnt = 0, it = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
+    uint32_t cnt = 0;
+    int mt, nt, b;
+    if (resident && tile_at(0, mt, nt, b)) {
+      ptx::mbar_wait(a_full, 0);
+      ptx::tc_fence_after();
+    }
+    for (int it = 0; tile_at(it, mt, nt, b); ++it) {
       const int a = it % ACC;
       ptx::mbar_wait(&tmem_empty[a], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
       ptx::tc_fence_after();
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
-        const int s = cnt % STAGES;
-        ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
+        const int s = cnt % nst;
+        ptx::mbar_wait(&full_bar[s], (cnt / nst) & 1);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t st = ptx::smem_u32(ring + s * ring_stage);
+        const uint32_t sa = resident ? ptx::smem_u32(smem + kc * A_BYTES) : st;
+        const uint32_t sb = resident ? st : st + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t db = ptx::umma_desc(sb + k * 2048, BK * 128, 1024);
@@ -232,10 +281,8 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     const int h = e >> 2;            // column half [128 h, 128 h + 128) of the 256-frame tile handled by this warp
     uint8_t* stg = stg_base + e * STG_BYTES;
     const uint32_t stg_row = ptx::smem_u32(stg) + lane * 128;
-    uint32_t it = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += npairs, ++it) {
-      const int mt = tile % p.m_tiles, rest = p.rev ? p.num_tiles / p.m_tiles - 1 - tile / p.m_tiles : tile / p.m_tiles;
-      const int nt = rest % p.n_tiles, b = rest / p.n_tiles;
+    int mt, nt, b;
+    for (uint32_t it = 0; tile_at((int)it, mt, nt, b); ++it) {
       const int t0 = nt * BN + h * 128;
       const int mrow0 = mt * BM + (int)rank * 128 + q * 32;
       const int m = mrow0 + lane;
@@ -348,6 +395,8 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
 
 }  // namespace pw3
 
+int option_pw_resident();
+
 // bf16-row outputs with Cout > 128 on CTA pairs; TS_ERR_UNSUPPORTED otherwise (caller falls back)
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
@@ -380,6 +429,14 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   p.stats = stats;
   p.f16 = f16;
   p.rev = next_walk_reversed();
+  // Weight-stationary mode (option pw_resident, OFF by default): all k-chunks of this CTA's weight rows stay in shared
+  // memory (K <= 512) and the ring streams activations only.  It removes the weight re-reads (~40 % of the L2 -> SM bytes
+  // of a 512 x 512 layer) but leaves room for only 4 activation stages of 16 KB: measured on B200 (ncu, 512 x 512 layer at
+  // 256 x 751 frames) 90.2 -> 99.4 us, tensor pipe 64 -> 56 % busy, L2 throughput 43 -> 30 % of peak -- the kernel is bound
+  // by bytes in flight, not by L2 bandwidth, so the 6 x 32 KB ring stays the default.
+  const int kc_total = p.kc0 + p.kc1;
+  p.res_kc = (option_pw_resident() && kc_total <= pw3::UNITS - 4) ? kc_total : 0;
+  p.nst = p.res_kc ? pw3::UNITS - p.res_kc : pw3::STAGES;
   p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
   static int num_sms = 0;
   if (num_sms == 0) {

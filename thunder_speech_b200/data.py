@@ -41,9 +41,11 @@ def sinc_resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int 
     return (k * window * (base / o)).astype(np.float32), width, o, n
 
 
-def pcm_ingest(pcm: Tensor, lens: Optional[Tensor] = None, interleaved: bool = False, remove_dc: bool = True) -> Tensor:
+def pcm_ingest(pcm: Tensor, lens: Optional[Tensor] = None, interleaved: bool = False, remove_dc: bool = True,
+               out: Optional[Tensor] = None) -> Tensor:
     """``pcm``: int16 or float32 CUDA tensor ``[B, channels, N]`` (or ``[B, N, channels]`` with ``interleaved``) ->
-    float32 ``[B, N]``: mono mix, int16 scaled by 1/32768, per-utterance DC removed, zero beyond ``lens``."""
+    float32 ``[B, N]``: mono mix, int16 scaled by 1/32768, per-utterance DC removed, zero beyond ``lens``.  ``out``: an
+    existing contiguous float32 ``[B, N]`` buffer to write into (e.g. the input buffer of a captured graph)."""
     if not pcm.is_cuda:
         raise RuntimeError("thunder_b200 ingest runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
     if pcm.dim() != 3:
@@ -54,7 +56,10 @@ def pcm_ingest(pcm: Tensor, lens: Optional[Tensor] = None, interleaved: bool = F
     B = pcm.shape[0]
     C, N = (pcm.shape[2], pcm.shape[1]) if interleaved else (pcm.shape[1], pcm.shape[2])
     l32 = lens.to(device=pcm.device, dtype=torch.int32).contiguous() if lens is not None else None
-    out = torch.empty((B, N), device=pcm.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, N), device=pcm.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (B, N) or not out.is_contiguous() or out.device != pcm.device:
+        raise ValueError("pcm_ingest: out must be a contiguous float32 [B, N] tensor on the device of pcm")
     nscr = B * ((N + 65535) // 65536)
     scratch = torch.empty((nscr,), device=pcm.device, dtype=torch.float64)
     _lib.check(_lib.lib().ts_pcm_ingest(pcm.data_ptr(), _lib.TS_I16 if pcm.dtype == torch.int16 else _lib.TS_F32, B, C, N,

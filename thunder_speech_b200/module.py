@@ -242,12 +242,18 @@ class CTCModule(nn.Module):
     @torch.no_grad()
     def to_torchscript(self, example_audio: Tensor, example_lengths: Optional[Tensor] = None,
                        file_path: Optional[str] = None) -> "torch.jit.ScriptModule":
-        """TorchScript export of ``forward`` (audio, lengths) -> (logits, lengths), the counterpart of Lightning's
-        ``to_torchscript`` the reference relies on.  It is produced by TRACING: the graph is a sequence of
-        ``torch.ops.thunder_b200.*`` calls, runs any batch size, but is specialised to the audio LENGTH of the example (frame
-        counts are Python ints at trace time).  ``torch.jit.script`` is not offered -- the reference's own front-end does not
-        script on torch 2.x either.  Loading in a fresh process needs ``import thunder_speech_b200.ops``
-        first so that the custom ops are registered."""
+        """TorchScript export with the reference's two entry points (Lightning's ``to_torchscript`` on ``BaseCTCModule``:
+        ``forward`` plus the ``@torch.jit.export``-ed ``predict``, src/thunder/module.py:74-100):
+
+            ts = module.to_torchscript(example_audio)
+            logits, out_lengths = ts(audio, lengths)
+            texts = ts.predict(audio)                  # List[str], greedy CTC incl. detokenisation, inside TorchScript
+
+        The kernels enter the graph by TRACING (a sequence of ``torch.ops.thunder_b200.*`` calls; any batch size, but the frame
+        counts are Python ints at trace time, so the export is specialised to the audio LENGTH of the example); the
+        detokeniser is a scripted module with the reference's string rules.  ``torch.jit.script`` of the whole model is not
+        offered -- the reference's own front-end does not script on torch 2.x either.  Loading in a fresh
+        process needs ``import thunder_speech_b200.ops`` first so that the custom ops are registered."""
         import warnings
 
         if example_lengths is None:
@@ -256,14 +262,26 @@ class CTCModule(nn.Module):
         self.eval()
         with torch.no_grad(), warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            traced = torch.jit.trace(self, (example_audio, example_lengths), check_trace=False)
+            traced = torch.jit.trace_module(self, {"forward": (example_audio, example_lengths),
+                                                   "_predict_collapsed": (example_audio,)}, check_trace=False)
+            v = self.text_transform.vocab
+            specials = [v.blank_token, v.pad_token] + [t for t in (v.start_token, v.end_token) if t is not None]
+            exported = torch.jit.script(_TorchScriptExport(traced, list(v.itos), specials))
         self.train(was_training)
         if file_path is not None:
-            torch.jit.save(traced, file_path)
-        return traced
+            torch.jit.save(exported, file_path)
+        return exported
 
-    def predict_stream(self, batches: Iterable[Tensor], depth: int = 3) -> Iterator[List[str]]:
-        """Serving loop over HOST batches ``[B, N]`` of one fixed shape (pinned memory for true overlap): the
+    def _predict_collapsed(self, x: Tensor) -> Tuple[Tensor, Tensor]:
+        """Traceable device part of ``predict``: (collapsed ids ``[B, T']`` padded with -1, counts ``[B]``)."""
+        _, col, cnt = self.predict_ids(x)
+        return col, cnt
+
+    def predict_stream(self, batches: Iterable[Tensor], depth: int = 3, remove_dc: bool = False) -> Iterator[List[str]]:
+        """Serving loop over HOST batches ``[B, N]`` of one fixed shape (pinned memory for true overlap): float32 audio
+        like ``predict``, or **int16 PCM** as it comes out of a wav file -- half the host-to-device bytes; the samples are
+        scaled by 1/32768 on the device like ``torchaudio.load`` does on the host (``ts_pcm_ingest``; ``remove_dc`` also
+        subtracts the per-utterance mean like ``AudioFileLoader.preprocess_audio``, src/thunder/data/dataset.py:50-77).  The
         host-to-device copies run on a copy stream ahead of the compute (CUDA-graph replay) and the detokenisation of
         finished batches runs on the CPU meanwhile.  ``depth`` batches are in flight: with 3 the copy of batch i+1 is
         queued before the host waits for batch i-1, so it has a whole step to finish even when the PCIe transfer takes
@@ -276,10 +294,10 @@ class CTCModule(nn.Module):
             if pipe is None:
                 # staging buffers, pinned result buffers and the captured graph are kept per (shape, depth): building
                 # them costs ~20 ms (cudaHostAlloc, graph warm-up), which a short stream would pay on every call
-                key = (tuple(xb.shape), depth)
+                key = (tuple(xb.shape), depth, xb.dtype, bool(remove_dc))
                 pipe = self._pipes.get(key)
                 if pipe is None:
-                    pipe = self._pipes[key] = _StreamPipe(self, xb, depth)
+                    pipe = self._pipes[key] = _StreamPipe(self, xb, depth, remove_dc)
                 pipe.reset()
             pending.append(pipe.submit(i, xb))
             if len(pending) == depth:
@@ -288,16 +306,53 @@ class CTCModule(nn.Module):
             yield pipe.collect(pending.pop(0))
 
 
+class _TorchScriptExport(nn.Module):
+    """What ``CTCModule.to_torchscript`` returns (scripted): ``forward`` = the traced kernel sequence, ``predict`` = traced
+    greedy-CTC ids + the reference's detokenisation rules (text_processing/transform.py:93-122, vocab.py:85-130)."""
+
+    def __init__(self, traced: torch.nn.Module, itos: List[str], specials: List[str]):
+        super().__init__()
+        self.traced = traced
+        self.itos = itos
+        self.specials = specials
+
+    def forward(self, x: Tensor, lengths: Tensor) -> Tuple[Tensor, Tensor]:
+        return self.traced(x, lengths)
+
+    @torch.jit.export
+    def predict(self, x: Tensor) -> List[str]:
+        col, cnt = self.traced._predict_collapsed(x)
+        col = col.cpu()
+        cnt = cnt.cpu()
+        out: List[str] = []
+        for b in range(col.size(0)):
+            s = ""
+            for t in range(int(cnt[b])):
+                s += self.itos[int(col[b, t])]
+            s = s.replace("\u2581", " ")      # sentencepiece word boundary
+            s = s.replace("|", " ")           # huggingface word boundary
+            for sp in self.specials:          # blank, pad (, start, end) removed as SUBSTRINGS, in the reference's order
+                s = s.replace(sp, "")
+            out.append(s)
+        return out
+
+
 class _StreamPipe:
     """Multi-buffered H2D / compute / D2H pipeline behind :meth:`CTCModule.predict_stream`."""
 
-    def __init__(self, module: CTCModule, example: Tensor, depth: int = 3):
+    def __init__(self, module: CTCModule, example: Tensor, depth: int = 3, remove_dc: bool = False):
         self.m = module
         self.depth = depth
+        self.remove_dc = remove_dc
+        if example.dtype not in (torch.float32, torch.int16):
+            raise TypeError("predict_stream: batches must be float32 audio or int16 PCM")
+        self.pcm = example.dtype == torch.int16
         dev = next(module.encoder.parameters()).device
         B, N = example.shape
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.stage = [torch.empty((B, N), device=dev, dtype=torch.float32) for _ in range(depth)]
+        # int16 PCM lands here (half the PCIe bytes) and one ingest kernel converts it into the graph's float32 input
+        self.stage16 = [torch.empty((B, 1, N), device=dev, dtype=torch.int16) for _ in range(depth)] if self.pcm else None
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
         self.stage_free = [torch.cuda.Event() for _ in range(depth)]
         self.d2h_done = [torch.cuda.Event() for _ in range(depth)]
@@ -320,9 +375,16 @@ class _StreamPipe:
         with torch.cuda.stream(self.copy_stream):
             if i >= self.depth:
                 self.copy_stream.wait_event(self.stage_free[s])
-            self.stage[s].copy_(xb, non_blocking=True)
+            if self.pcm:
+                self.stage16[s].copy_(xb.view(self.stage16[s].shape), non_blocking=True)
+            else:
+                self.stage[s].copy_(xb, non_blocking=True)
             self.h2d_done[s].record(self.copy_stream)
         cur.wait_event(self.h2d_done[s])
+        if self.pcm:
+            from .data import pcm_ingest
+
+            pcm_ingest(self.stage16[s], None, False, self.remove_dc, out=self.stage[s])
         _, col, cnt = self.m.predict_ids_graphed(self.stage[s], in_place=self.in_place)
         self.stage_free[s].record(cur)
         self.host_col[s].copy_(col, non_blocking=True)
