@@ -76,6 +76,27 @@ int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemp
               const float* mel_w, int nfilt, int nnz,
               float* logmel, void* stream);
 
+/* The same three stages with the STFT as a DFT-MATRIX CONTRACTION on the tensor cores (tcgen05, CTA pairs; the
+ * reference's own DFT-matrix STFT is src/thunder/blocks.py:38-91): n_fft = 512 with the window supported on [96, 416)
+ * only.  The frame is folded about n = 255.5 (y+[m] = y[256+m], y-[m] = y[255-m], m < 160), so
+ * |X[k]|^2 = (sum_m (y+ + y-)[m] cos(th))^2 + (sum_m (y+ - y-)[m] sin(th))^2, th = 2 pi k (m + 1/2) / 512: two real GEMMs
+ * [frames x 160] x [160 x 256]; operands are fp16 hi/lo splits (3 MMAs per product, ~22 mantissa bits).
+ *   wplus/wminus [160] f32 = window_full[256 + m] / window_full[255 - m]
+ *   basis   2 x 163840 bytes: for CTA rank r in {0,1}: matrices C_hi, C_lo, S_hi, S_lo, each 10 k-steps of a
+ *           [128 bins (128 r + n) x 16 m] fp16 slice in the no-swizzle K-major core-matrix layout
+ *           (byte offset of (n, k) = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2); C = cos(th), S = sin(th) except
+ *           S[m][bin 0] = (-1)^m, which makes sine column 0 carry bin 256
+ *   mel_w2  [257][2] f32, mel_adv [257] i32: the filter bank as a SLIDING two-filter window over the ordered bins: before
+ *           bin k is accumulated, mel_adv[k] filters are complete and emitted; mel_w2[k] = weights of bin k for the current
+ *           and the next filter (requires every bin to touch at most two consecutive filters)
+ *   logmel  [B, nfilt, F] f32 out;  partials (nullable) [B, ceil(F/32), nfilt, 2] f32: sum / sum of squares of the
+ *           log-mel values over the valid frames (f < lengths[b] / hop + 1; lengths nullable = all) of each 32-frame
+ *           group, consumed by ts_feature_normalize's `partials` path
+ * |window * audio| must stay below 255 (fp16 operand range after the 2^8 scaling): float audio in [-1, 1]. */
+int ts_logmel_dft(const float* audio, int B, int N, int hop, float preemph, const float* wplus, const float* wminus,
+                  const void* basis, const float* mel_w2, const int32_t* mel_adv, int nfilt, float* logmel,
+                  float* partials, const int64_t* lengths, void* stream);
+
 /* Replaces PowerSpectrum.get_sequence_length (transform.py:182-184) + FeatureBatchNormalizer.forward
  * (transform.py:77-92 -> src/thunder/blocks.py:118-149): seq_len = floor(len/hop)+1; per (b, feature)
  * masked mean / biased std over t < seq_len, (x-mean)/(std+div_guard), zero for t >= seq_len.
@@ -84,6 +105,12 @@ int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemp
 int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int nfilt, int F, int hop,
                          float div_guard, void* out, int out_dtype, int out_pitch,
                          int64_t* seq_len_out, void* stream);
+
+/* The same from the partial sums of ts_logmel_dft (`partials` [B, ceil(F/32), nfilt, 2] f32: sum / sum of squares of the
+ * valid log-mel frames per 32-frame group): one streaming pass over the log-mel tensor, no reduction pass. */
+int ts_feature_normalize_partials(const float* logmel, const float* partials, const int64_t* lengths, int B, int nfilt,
+                                  int F, int hop, float div_guard, void* out, int out_dtype, int out_pitch,
+                                  int64_t* seq_len_out, void* stream);
 
 /* ---- (2) masked depthwise conv1d ----------------------------------------------------------- */
 /* Replaces MaskedConv1d.forward with groups == channels (src/thunder/quartznet/blocks.py:158-182; built by

@@ -183,3 +183,60 @@ def test_spec_augment_under_cuda_graph_capture_uses_device_draws():
         assert int(tcols.sum()) <= 2 * 40 and int(frows.sum()) <= 12
         patterns.append(z[0].cpu())
     assert any(not torch.equal(patterns[0], p) for p in patterns[1:])
+
+
+@pytest.fixture
+def dft_kernel():
+    import thunder_speech_b200 as tsb
+
+    old = tsb.get_stft_kernel()
+    tsb.set_stft_kernel("dft")
+    yield
+    tsb.set_stft_kernel(old)
+
+
+@pytest.mark.parametrize("name,kind", FEATURE_CASES)
+def test_dft_tensor_core_frontend_vs_golden_and_oracle(golden_features, dft_kernel, name, kind):
+    """Variant B of north_star kernel 1 -- the STFT as a DFT-matrix contraction on tcgen05 with split-fp16 operands
+    (csrc/featdft.cu; the reference's own DFT-matrix STFT: src/thunder/blocks.py:38-91, pinned by tests/test_blocks.py:15-30)
+    and the normaliser fed by the kernel's partial sums: same 1e-4 bar against the reference's goldens and the oracle,
+    ragged lengths, lengths exact."""
+    g = golden_features
+    nfilt, B, N, seed = [int(v) for v in g[f"{name}.meta"]]
+    x = synth.audio(B, N, seed, kind)
+    lens = synth.ragged_lengths(B, N, seed + 100)
+    f, fl = run_cuda(x, lens, nfilt)
+    assert np.array_equal(fl, g[f"{name}.lengths"])
+    emax, el2 = rel_err(f, g[f"{name}.features"])
+    assert emax < TOL and el2 < TOL, (emax, el2)
+    rf, _ = R.filterbank_features(x, lens, nfilt=nfilt)
+    emax, el2 = rel_err(f, rf)
+    assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+@pytest.mark.parametrize("N", [257, 1600, 5121, 256 * 160 - 1, 256 * 160 + 161, 3 * 256 * 160 + 77])
+def test_dft_frontend_ragged_shapes_and_rows(dft_kernel, N):
+    """256-frame pair-tile edges, reflect padding at both ends, masked / empty utterances; the 16-bit row outputs of the
+    two front-ends agree (what the encoder consumes); a window the DFT kernel does not implement falls back to the FFT."""
+    import thunder_speech_b200 as tsb
+    from thunder_speech_b200 import ops
+
+    x = synth.audio(3, N, N, "tones")
+    lens = np.array([N, max(1, N // 2), 0], np.int64)
+    f, fl = run_cuda(x, lens)
+    rf, rl = R.filterbank_features(x, lens)
+    assert np.array_equal(fl, rl) and np.isfinite(f).all()
+    emax, el2 = rel_err(f, rf)
+    assert emax < TOL and el2 < TOL, (N, emax, el2)
+    fb = FilterbankFeatures().eval().cuda()
+    F = 1 + N // 160
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda()
+    rows_dft, _ = fb.features(xd, ld, bf16_pitch=ops.row_pitch(F))
+    tsb.set_stft_kernel("fft")
+    rows_fft, _ = fb.features(xd, ld, bf16_pitch=ops.row_pitch(F))
+    tsb.set_stft_kernel("dft")
+    d = (rows_dft.float() - rows_fft.float()).abs().max()
+    assert float(d) <= 2.0 ** -6, float(d)            # bf16 rounding of values that differ by <= 1e-4 relative
+    f2, _ = run_cuda(x[:, :6000] if N >= 6000 else x, np.minimum(lens, 6000), 64, n_window_size=400)
+    r2, _ = R.filterbank_features(x[:, :6000] if N >= 6000 else x, np.minimum(lens, 6000), n_window_size=400)
+    assert max(rel_err(f2, r2)) < TOL

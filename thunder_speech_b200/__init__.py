@@ -47,3 +47,24 @@ def row_dtype(precision=None):
     if precision not in _PRECISIONS:
         raise ValueError(f"precision must be one of {_PRECISIONS}, got {precision!r}")
     return torch.float16 if precision == "fp16" else torch.bfloat16
+
+
+#: STFT kernel of the feature front-end: "dft" = DFT-matrix contraction on the tensor cores (tcgen05, split-fp16 operands;
+#: n_fft 512 with the window supported on [96, 416), float audio within [-255, 255]) with automatic fall-back to "fft" = the
+#: shared-memory radix-8 FFT (any window / filter bank / amplitude).  Both hold the 1e-4 feature parity; see DESIGN.md for
+#: the ncu A/B that picked the default.
+_STFT_KERNELS = ("fft", "dft")
+_stft_kernel = _os.environ.get("THUNDER_B200_STFT", "fft")
+if _stft_kernel not in _STFT_KERNELS:
+    raise ValueError(f"THUNDER_B200_STFT must be one of {_STFT_KERNELS}, got {_stft_kernel!r}")
+
+
+def set_stft_kernel(kind: str) -> None:
+    global _stft_kernel
+    if kind not in _STFT_KERNELS:
+        raise ValueError(f"stft kernel must be one of {_STFT_KERNELS}, got {kind!r}")
+    _stft_kernel = kind
+
+
+def get_stft_kernel() -> str:
+    return _stft_kernel

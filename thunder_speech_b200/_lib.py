@@ -38,8 +38,12 @@ SIGNATURES = {
     "ts_set_option": (c_int, [c_char_p, c_int]),
     "ts_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ts_logmel_dft": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_feature_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
                                      c_int, c_void_p, c_void_p]),
+    "ts_feature_normalize_partials": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                              c_int, c_int, c_void_p, c_void_p]),
     "ts_dw_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                            c_int, c_void_p, c_int, c_void_p]),
     "ts_pw_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

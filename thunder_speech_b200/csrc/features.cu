@@ -358,10 +358,67 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
   }
 }
 
+// Same normalisation from the per-(32 frames, filter) partial sums the DFT front-end emits (ts_logmel_dft): no reduction
+// pass over the log-mel tensor -- 4 warps per (b, filter) row each re-derive mean / std from <= 64 partials and stream a
+// quarter of the row.  sum (x - mean)^2 over the valid frames = S2 - n mean^2; the reference's (0 - mean)^2 term of every
+// masked frame is added like in normalize_rows_kernel.
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+normalize_partials_kernel(const float* __restrict__ logmel, const float* __restrict__ partials, int pslots,
+                          const int64_t* __restrict__ lengths, int nfilt, int F, int hop, float div_guard,
+                          OutT* __restrict__ out, int out_pitch, int64_t* __restrict__ seq_len_out) {
+  const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = row / nfilt, m = row - b * nfilt;
+  const int64_t len = lengths[b];
+  const int64_t q = len >= 0 ? len / hop : -((-len + hop - 1) / hop);
+  const int64_t seq = q + 1;
+  if (seq_len_out != nullptr && m == 0 && threadIdx.x == 0) seq_len_out[b] = seq;
+  const int n = (int)(seq < 0 ? 0 : (seq > F ? F : seq));
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = lane; i < pslots; i += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(partials + (((size_t)b * pslots + i) * nfilt + m) * 2);
+    s1 += (double)v.x;
+    s2 += (double)v.y;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float mean = (float)(s1 / (double)n);
+  const double md = (double)mean;
+  double ss = s2 - 2.0 * md * s1 + (double)n * md * md + (double)(F - n) * md * md;
+  if (ss < 0.0) ss = 0.0;
+  const float den = (float)sqrt(ss / (double)n) + div_guard;
+  const float* in = logmel + (size_t)row * F;
+  OutT* o = out + (size_t)row * out_pitch;
+  for (int t = threadIdx.x; t < out_pitch; t += 128) store_out(o + t, (t < n) ? (in[t] - mean) / den : 0.f);
+  (void)warp;
+}
+
 }  // namespace feat
 }  // namespace ts
 
 using namespace ts;
+
+extern "C" int ts_feature_normalize_partials(const float* logmel, const float* partials, const int64_t* lengths, int B,
+                                             int nfilt, int F, int hop, float div_guard, void* out, int out_dtype,
+                                             int out_pitch, int64_t* seq_len_out, void* stream) {
+  TS_REQUIRE(logmel && partials && lengths && out, TS_ERR_INVALID, "ts_feature_normalize_partials: null pointer");
+  TS_REQUIRE(B > 0 && nfilt > 0 && F > 0 && hop > 0 && out_pitch >= F, TS_ERR_INVALID, "ts_feature_normalize_partials: bad sizes");
+  TS_REQUIRE(out_dtype == TS_F32 || out_dtype == TS_BF16 || out_dtype == TS_F16, TS_ERR_INVALID,
+             "ts_feature_normalize_partials: bad dtype %d", out_dtype);
+  const int rows = B * nfilt, pslots = ceil_div(F, 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == TS_F32)
+    feat::normalize_partials_kernel<float><<<rows, 128, 0, st>>>(logmel, partials, pslots, lengths, nfilt, F, hop, div_guard,
+                                                                 (float*)out, out_pitch, seq_len_out);
+  else if (out_dtype == TS_F16)
+    feat::normalize_partials_kernel<__half><<<rows, 128, 0, st>>>(logmel, partials, pslots, lengths, nfilt, F, hop, div_guard,
+                                                                  (__half*)out, out_pitch, seq_len_out);
+  else
+    feat::normalize_partials_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(logmel, partials, pslots, lengths, nfilt, F, hop,
+                                                                         div_guard, (__nv_bfloat16*)out, out_pitch, seq_len_out);
+  TS_LAUNCH_CHECK("normalize_partials_kernel");
+  return TS_OK;
+}
 
 extern "C" int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemph,
                          const float* window_full, int win_lo, int win_hi, const float* twiddle,

@@ -120,6 +120,49 @@ def _(audio, lengths, window_full, twiddle, mel_start, mel_count, mel_off, mel_w
     return out, audio.new_empty((B,), dtype=torch.int64)
 
 
+@torch.library.custom_op(f"{NS}::filterbank_dft", mutates_args=())
+def filterbank_dft(audio: Tensor, lengths: Tensor, wplus: Tensor, wminus: Tensor, basis: Tensor, mel_w2: Tensor,
+                   mel_adv: Tensor, nfilt: int, hop: int, preemph: float, div_guard: float, out_bf16_pitch: int,
+                   out_f16: bool = False) -> Tuple[Tensor, Tensor]:
+    """Eval-mode ``FilterbankFeatures`` with the STFT as a DFT-matrix contraction on the tensor cores (``ts_logmel_dft``,
+    n_fft 512 / window support [96, 416) only) and the normaliser fed by the partial sums that kernel emits
+    (``ts_feature_normalize_partials``).  Same outputs as :func:`filterbank`."""
+    _need_cuda(audio, lengths, wplus, wminus, basis, mel_w2, mel_adv)
+    if audio.dim() != 2:
+        raise ValueError("audio must be [batch, time]")
+    audio = audio.contiguous().float()
+    B, N = audio.shape
+    F = 1 + N // hop
+    lens64 = lengths.to(torch.int64).contiguous()
+    L = _lib.lib()
+    logmel = torch.empty((B, nfilt, F), device=audio.device, dtype=torch.float32)
+    partials = torch.empty((B, (F + 31) // 32, nfilt, 2), device=audio.device, dtype=torch.float32)
+    _lib.check(L.ts_logmel_dft(_ptr(audio), B, N, hop, preemph, _ptr(wplus), _ptr(wminus), _ptr(basis), _ptr(mel_w2),
+                               _ptr(mel_adv), nfilt, _ptr(logmel), _ptr(partials), _ptr(lens64), _stream()), "ts_logmel_dft")
+    seq = torch.empty((B,), device=audio.device, dtype=torch.int64)
+    if out_bf16_pitch > 0:
+        out = torch.empty((B, nfilt, out_bf16_pitch), device=audio.device,
+                          dtype=torch.float16 if out_f16 else torch.bfloat16)
+        dt, pitch = (_lib.TS_F16 if out_f16 else _lib.TS_BF16), out_bf16_pitch
+    else:
+        out = torch.empty((B, nfilt, F), device=audio.device, dtype=torch.float32)
+        dt, pitch = _lib.TS_F32, F
+    _lib.check(L.ts_feature_normalize_partials(_ptr(logmel), _ptr(partials), _ptr(lens64), B, nfilt, F, hop, div_guard,
+                                               _ptr(out), dt, pitch, _ptr(seq), _stream()), "ts_feature_normalize_partials")
+    return out, seq
+
+
+@filterbank_dft.register_fake
+def _(audio, lengths, wplus, wminus, basis, mel_w2, mel_adv, nfilt, hop, preemph, div_guard, out_bf16_pitch, out_f16=False):
+    B, N = audio.shape
+    F = 1 + N // hop
+    if out_bf16_pitch > 0:
+        out = audio.new_empty((B, nfilt, out_bf16_pitch), dtype=torch.float16 if out_f16 else torch.bfloat16)
+    else:
+        out = audio.new_empty((B, nfilt, F), dtype=torch.float32)
+    return out, audio.new_empty((B,), dtype=torch.int64)
+
+
 # ------------------------------------------------------------------------------------------- layout
 def row_pitch(T: int) -> int:
     """Pitch (frames) of a padded bf16 activation row holding T frames (multiple of 64)."""

@@ -174,8 +174,69 @@ class _FusedFilterbank(nn.Sequential):
             mel_w=torch.tensor(weights, dtype=torch.float32, device=device),
             win_lo=win_lo, win_hi=win_hi,
         )
+        t.update(self._dft_tables(wfull, win_lo, win_hi, fb, device))
         self._tables = (key, t)
         return t
+
+    @staticmethod
+    def _dft_tables(wfull: np.ndarray, win_lo: int, win_hi: int, fb: np.ndarray, device) -> dict:
+        """Operands of the tensor-core DFT front-end (``ts_logmel_dft``): folded window taps, the split cosine / sine basis
+        in the kernel's shared-memory layout, and the filter bank as a sliding two-filter window.  ``dft_ok`` is False when
+        the configuration is outside what that kernel implements (then the FFT kernel runs)."""
+        n_fft, KM, KS = wfull.shape[0], 160, 10
+        ok = n_fft == 512 and win_lo >= 96 and win_hi <= 416 and fb.shape[1] == 257 and fb.shape[0] <= 128
+        # sliding window: bin k may only touch filters {j_k, j_k + 1}, j_k non-decreasing
+        nf = fb.shape[0]
+        w2 = np.zeros((257, 2), np.float32)
+        adv = np.zeros(257, np.int32)
+        j = 0
+        for k in range(257 if ok else 0):
+            nzf = np.nonzero(fb[:, k])[0]
+            if nzf.size:
+                jk = int(nzf[0])
+                if jk < j:   # an earlier filter is touched again (its accumulator is gone): not a sliding bank
+                    if int(nzf[-1]) > j + 1 or jk < j:
+                        ok = False
+                        break
+                if int(nzf[-1]) > max(jk, j) + 1:
+                    ok = False
+                    break
+                jk = max(jk, j)
+                adv[k] = jk - j
+                j = jk
+                w2[k, 0] = fb[j, k]
+                if j + 1 < nf:
+                    w2[k, 1] = fb[j + 1, k]
+        if not ok:
+            return dict(dft_ok=False)
+        m = np.arange(KM, dtype=np.float64)
+        k = np.arange(256, dtype=np.float64)
+        th = 2.0 * np.pi * np.outer(k, m + 0.5) / n_fft           # [bin, m]
+        C, S = np.cos(th), np.sin(th)
+        S[0, :] = (-1.0) ** np.arange(KM)                          # sine column 0 carries bin 256
+
+        def split(a):
+            hi = a.astype(np.float16)
+            lo = (a - hi.astype(np.float64)).astype(np.float16)
+            return hi, lo
+
+        mats = [*split(C), *split(S)]                              # C_hi, C_lo, S_hi, S_lo
+        basis = np.zeros((2, 4, KS, 128 * 16), np.float16)
+        n = np.arange(128)
+        kk = np.arange(16)
+        off = ((n[:, None] // 8) * 256 + (kk[None, :] // 8) * 128 + (n[:, None] % 8) * 16 + (kk[None, :] % 8) * 2) // 2
+        for r in range(2):
+            for mi, a in enumerate(mats):
+                for ks in range(KS):
+                    basis[r, mi, ks, off.reshape(-1)] = a[128 * r:128 * r + 128, 16 * ks:16 * ks + 16].reshape(-1)
+        return dict(
+            dft_ok=True,
+            wplus=torch.from_numpy(np.ascontiguousarray(wfull[256:256 + KM])).to(device),
+            wminus=torch.from_numpy(np.ascontiguousarray(wfull[255 - KM + 1:256][::-1])).to(device),
+            basis=torch.from_numpy(basis.view(np.uint8).reshape(-1).copy()).to(device),
+            mel_w2=torch.from_numpy(w2).to(device),
+            mel_adv=torch.from_numpy(adv).to(device),
+        )
 
     def features(self, audio: Tensor, lengths: Tensor, bf16_pitch: int = 0, f16: bool = False) -> Tuple[Tensor, Tensor]:
         """Run the fused front-end.  ``bf16_pitch > 0`` emits 16-bit padded rows for the encoder kernels (bf16, or fp16
@@ -190,10 +251,19 @@ class _FusedFilterbank(nn.Sequential):
             if self.training and dither.dither != 0:
                 audio = dither(audio)
             t = self._device_tables(audio.device)
-            feats, feat_len = torch.ops.thunder_b200.filterbank(
-                audio, lengths, t["window_full"], t["twiddle"], t["mel_start"], t["mel_count"], t["mel_off"],
-                t["mel_w"], ps.hop_length, float(pre.preemph), t["win_lo"], t["win_hi"], float(norm.div_guard),
-                int(bf16_pitch), bool(f16))
+            from .. import get_stft_kernel
+
+            if get_stft_kernel() == "dft" and t["dft_ok"] and audio.shape[-1] > ps.n_fft // 2:
+                # STFT as a DFT-matrix contraction on the tensor cores + normaliser fed by that kernel's partial sums
+                feats, feat_len = torch.ops.thunder_b200.filterbank_dft(
+                    audio, lengths, t["wplus"], t["wminus"], t["basis"], t["mel_w2"], t["mel_adv"],
+                    t["mel_start"].numel(), ps.hop_length, float(pre.preemph), float(norm.div_guard), int(bf16_pitch),
+                    bool(f16))
+            else:   # shared-memory radix-8 FFT (any window inside n_fft = 512, any filter bank)
+                feats, feat_len = torch.ops.thunder_b200.filterbank(
+                    audio, lengths, t["window_full"], t["twiddle"], t["mel_start"], t["mel_count"], t["mel_off"],
+                    t["mel_w"], ps.hop_length, float(pre.preemph), t["win_lo"], t["win_hi"], float(norm.div_guard),
+                    int(bf16_pitch), bool(f16))
             if self.training and len(self) > 4:   # SpecCutout / SpecAugment: in place on the fresh feature tensor
                 from .spec_augment import apply_rects
 
