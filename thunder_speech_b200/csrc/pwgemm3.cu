@@ -52,6 +52,7 @@ struct Params {
                       // memory for the whole kernel (every pair owns ONE m-tile) and the ring streams activations only
   int nst;            // ring stages (6 x 32 KB streaming, 12 - res_kc x 16 KB weight-stationary)
   int rev;            // walk the (utterance, frame-tile) space from the far end (see next_walk_reversed())
+  int dbg;            // timing experiment: 32 = the epilogue only drains TMEM (no math, no stores)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -311,7 +312,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
             mbar_arrive_remote(&tmem_empty[a], 0);
         }
         const int tb = t0 + cc * 64;
-        if (mrow0 < p.Cout && tb < p.out_pitch) {   // warp-uniform: something of this 32 x 64 block is stored
+        if (mrow0 < p.Cout && tb < p.out_pitch && !(p.dbg & 32)) {   // warp-uniform: something of this 32 x 64 block is stored
           float r[64];
 #pragma unroll
           for (int j = 0; j < 64; ++j) r[j] = __uint_as_float(v[j]) + shift;
@@ -335,26 +336,24 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
           }
           if (lane == 0) bulk_wait_read0();   // previous TMA store has finished reading the staging tile
           __syncwarp();
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) r[j] = fmaxf(r[j], 0.f);
-          }
           if (tb + 64 > len) {   // block crosses the utterance end (warp-uniform): zero the tail
 #pragma unroll
             for (int j = 0; j < 64; ++j)
               if (tb + j >= len) r[j] = 0.f;
           }
-          // (uniform branch on the row format so that each path carries exactly one conversion per pair)
-          auto pack_and_stage = [&](auto f16_tag) {
-            constexpr bool kF16 = decltype(f16_tag)::value;
+          // (uniform branches on row format / activation so that each path carries exactly one conversion per pair; the
+          // ReLU rides in the conversion instruction: F2FP.RELU)
+          auto pack_and_stage = [&](auto f16_tag, auto relu_tag) {
+            constexpr bool kF16 = decltype(f16_tag)::value, kRelu = decltype(relu_tag)::value;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               uint32_t pk[4];
 #pragma unroll
               for (int hh = 0; hh < 4; ++hh) {
                 const int j = g * 8 + 2 * hh;
-                pk[hh] = kF16 ? pack_f16x2(r[j], r[j + 1]) : pack_bf16x2(r[j], r[j + 1]);
-                if (!kF16 && p.stats) {
+                pk[hh] = kF16 ? (kRelu ? pack_f16x2_relu(r[j], r[j + 1]) : pack_f16x2(r[j], r[j + 1]))
+                              : (kRelu ? pack_bf16x2_relu(r[j], r[j + 1]) : pack_bf16x2(r[j], r[j + 1]));
+                if (!kF16 && !kRelu && p.stats) {
                   const float2 f = unpack_bf16x2(pk[hh]);
                   st_s += f.x + f.y;
                   st_ss = fmaf(f.x, f.x, fmaf(f.y, f.y, st_ss));
@@ -366,10 +365,13 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
                            : "memory");
             }
           };
-          if (p.f16)
-            pack_and_stage(std::true_type{});
-          else
-            pack_and_stage(std::false_type{});
+          if (p.f16) {
+            if (p.relu) pack_and_stage(std::true_type{}, std::true_type{});
+            else pack_and_stage(std::true_type{}, std::false_type{});
+          } else {
+            if (p.relu) pack_and_stage(std::false_type{}, std::true_type{});
+            else pack_and_stage(std::false_type{}, std::false_type{});
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -429,6 +431,7 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   p.stats = stats;
   p.f16 = f16;
   p.rev = next_walk_reversed();
+  p.dbg = option_dbg();
   // Weight-stationary mode (option pw_resident, OFF by default): all k-chunks of this CTA's weight rows stay in shared
   // memory (K <= 512) and the ring streams activations only.  It removes the weight re-reads (~40 % of the L2 -> SM bytes
   // of a 512 x 512 layer) but leaves room for only 4 activation stages of 16 KB: measured on B200 (ncu, 512 x 512 layer at
