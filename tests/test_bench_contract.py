@@ -8,6 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r01_*.json")))
+LINES_R02 = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r02_*.json")))
 
 
 def _load(path):
@@ -57,3 +58,42 @@ def test_bench_line_contract(path):
     # value is the whole-job aggregate: audio seconds of all ranks / step time
     per_gpu = d["config"]["per_gpu_batch"] * d["config"]["seconds"]
     assert d["value"] == pytest.approx(per_gpu * d["n_gpus"] / (d["ms_per_step"] * 1e-3), rel=1e-3)
+
+
+@pytest.mark.parametrize("path", LINES_R02, ids=[os.path.basename(p) for p in LINES_R02])
+def test_bench_line_contract_round2(path):
+    """Round-2 lines: strong scaling by default (the configuration's batch is SHARDED over the GPUs), the Citrinet-1024 leg
+    on the default line, reference arms that say what they ran."""
+    d = _load(path)
+    if d.get("impl") == "reference_cuda":
+        assert d["config"]["note"].startswith("unmodified reference modules") and d["value"] > 0
+        assert "autocast_bf16" in d
+        return
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e"):
+        assert k in d, k
+    assert d["metric"] == "audio-sec/sec" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    if d.get("impl") == "reference":
+        c = d["cpu_baseline"]
+        assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] == d["value"] == d["e2e"]["value"]
+        assert d["config"]["sample_batch_per_step"] < d["config"]["global_batch"] and "bounded sample" in d["config"]["note"]
+        return
+    cfg = d["config"]
+    assert d["scaling"] in ("strong", "weak")
+    if d["scaling"] == "strong":      # per-GPU work shrinks with N: global batch fixed
+        assert cfg["per_gpu_batch"] * d["n_gpus"] >= cfg["global_batch"] > cfg["per_gpu_batch"] * (d["n_gpus"] - 1)
+    else:
+        assert cfg["global_batch"] == cfg["per_gpu_batch"] * d["n_gpus"]
+    assert d["value"] == pytest.approx(cfg["global_batch"] * cfg["seconds"] / (d["ms_per_step"] * 1e-3), rel=1e-3)
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.001
+    assert d["gpu_launches"] > 0 and d["dtype"] in ("bf16", "f16", "f32")
+    clk = d["clocks"]
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clk["reasons"])
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-6) and 0 < r["frac"] < 1
+    if "also" in d:                   # both networks of BASELINE.json's metric on one line
+        a = d["also"]["citrinet1024"]
+        assert a["value"] > 0 and a["e2e"]["value"] > 0 and a["roofline"]["frac"] > 0 and "Citrinet-1024" in a["config"]["workload"]
+    assert ("cpu_baseline" in d) == (d["n_gpus"] == 1 and "also" in d or d["n_gpus"] == 1 and "cpu_baseline" in d)
