@@ -54,6 +54,11 @@ int64_t ts_launch_count(void);
  * (measured: +1.7 % on the QuartzNet forward, +6 % on the training step),
  * "dw_tma" (default 1) = TMA-fed Toeplitz kernel for pre-masked inputs, "dw_base_offset" (descriptor experiment) */
 int ts_set_option(const char* name, int value);
+/* diagnostics: install a DEVICE buffer of `slots` x 32 uint64 words; every following launch of the pair GEMM / Toeplitz
+ * kernels takes the next slot and its first and last CTA stamp %globaltimer at fixed points of their life (layout:
+ * csrc/ts_common.cuh, reader: tools/trace_chain.py).  buffer = NULL switches tracing off.  No reference counterpart
+ * (the reference profiles with torch.profiler); used to break down the per-kernel latency of the captured graph. */
+int ts_trace(void* buffer, int slots);
 /* pitch (in frames) of a padded activation row holding T frames */
 int ts_row_pitch(int T);
 

@@ -12,6 +12,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_vo
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libthunder_b200.so")
+if os.environ.get("THUNDER_B200_TRACE_BUILD") == "1":     # diagnostics: the build with the phase-trace hooks (`make trace`)
+    LIB_PATH = os.path.join(_HERE, "libthunder_b200_trace.so")
 
 TS_OK = 0
 TS_ERR_INVALID = -1
@@ -36,6 +38,7 @@ SIGNATURES = {
     "ts_launch_count": (c_int64, []),
     "ts_row_pitch": (c_int, [c_int]),
     "ts_set_option": (c_int, [c_char_p, c_int]),
+    "ts_trace": (c_int, [c_void_p, c_int]),
     "ts_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ts_logmel_dft": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -31,6 +31,10 @@ static Option g_options[] = {
     {"dw_base_offset", {0}},
     {"dw_share_halo", {1}},
     {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
+    {"dwp_nbuf", {0}},        // persistent Toeplitz kernel: Toeplitz buffers (0 = auto: 2 when NQ <= 3), experiment
+    {"dwp_nstage", {0}},      // ... input stages (0 = auto)
+    {"small", {0}},           // small-footprint co-resident kernels: 0 never, 1 when B x pitch <= small_frames, 2 always
+    {"small_frames", {32768}},
     {"serpentine", {1}},      // alternate the utterance walk direction between consecutive launches (L2 reuse)
     {"dbg", {0}},             // scratch knob for experiments
 };
@@ -50,12 +54,41 @@ int option_dw_tma() { return opt("dw_tma").load(std::memory_order_relaxed); }
 int option_dw_base_offset() { return opt("dw_base_offset").load(std::memory_order_relaxed); }
 int option_dw_mma() { return opt("dw_mma").load(std::memory_order_relaxed); }
 int option_pw_big() { return opt("pw_big").load(std::memory_order_relaxed); }
+int small_footprint(long long frames) {
+  const int m = opt("small").load(std::memory_order_relaxed);
+  return m >= 2 || (m == 1 && frames <= (long long)opt("small_frames").load(std::memory_order_relaxed));
+}
+int option_dwp_nbuf() { return opt("dwp_nbuf").load(std::memory_order_relaxed); }
+int option_dwp_nstage() { return opt("dwp_nstage").load(std::memory_order_relaxed); }
 int option_serpentine() { return opt("serpentine").load(std::memory_order_relaxed); }
 int option_dbg() { return opt("dbg").load(std::memory_order_relaxed); }
 static std::atomic<unsigned> g_walk{0};
 int next_walk_reversed() { return option_serpentine() ? (int)(g_walk.fetch_add(1, std::memory_order_relaxed) & 1u) : 0; }
 
+static unsigned long long* g_trace = nullptr;
+static std::atomic<int> g_trace_slots{0}, g_trace_next{0};
+unsigned long long* trace_next_slot(int kernel_id, unsigned grid) {
+  if (g_trace == nullptr) return nullptr;
+  const int i = g_trace_next.fetch_add(1, std::memory_order_relaxed);
+  if (i >= g_trace_slots.load(std::memory_order_relaxed)) return nullptr;
+  (void)kernel_id; (void)grid;   // the header word is written by the traced CTA itself (launches may be under capture)
+  return g_trace + (size_t)i * 32;
+}
+
 }  // namespace ts
+
+extern "C" int ts_trace(void* buffer, int slots) {
+#if !TS_TRACE
+  if (buffer != nullptr) {
+    ts::set_error("ts_trace: this build has no trace hooks (make -C thunder_speech_b200/csrc trace -> libthunder_b200_trace.so)");
+    return TS_ERR_UNSUPPORTED;
+  }
+#endif
+  ts::g_trace = reinterpret_cast<unsigned long long*>(buffer);
+  ts::g_trace_slots.store(buffer ? slots : 0);
+  ts::g_trace_next.store(0);
+  return TS_OK;
+}
 
 extern "C" const char* ts_version(void) { return "thunder_b200 0.1 (sm_100a)"; }
 extern "C" const char* ts_last_error(void) { return ts::g_err; }

@@ -186,6 +186,7 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
 int launch_dw_persist(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                       const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16);
 int option_dw_persist();
+int small_footprint(long long frames);
 }
 using namespace ts;
 
@@ -220,7 +221,8 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
       const int W = pitch_in / 64, HL = ceil_div(P, 64), NQ = HL + 1 + (63 + P) / 64;
       const int HR = NQ - 1 - HL, R = W + (HL > HR ? HL : HR);
       const int tiles_per_chan = R > 0 && R <= 128 ? ceil_div(B, 128 / R) : 1 << 30;
-      if (option_dw_persist() >= 2 || (option_dw_persist() == 1 && (NQ > 3 || tiles_per_chan <= 8))) {
+      if (option_dw_persist() >= 2 ||
+          (option_dw_persist() == 1 && (NQ > 3 || tiles_per_chan <= 8 || small_footprint((long long)B * pitch_in)))) {
         const int rc = launch_dw_persist(xb, B, C, T_in, pitch_in, w, K, D, P, len_in, yb, pitch_out, st, f16);
         if (rc != TS_ERR_UNSUPPORTED) return rc;
       }

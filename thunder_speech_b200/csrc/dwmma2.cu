@@ -38,6 +38,8 @@ struct Params {
   int tiles_per_chan, tiles_per_cta;
   int f16;               // rows (and the Toeplitz blocks) are IEEE fp16 instead of bf16
   int rev;               // walk the utterance tiles from the far end (see next_walk_reversed())
+  unsigned long long* trace;   // ts_trace slot of this launch (nullptr: off)
+  int dbg;               // timing experiments (results are wrong): 1 = one MMA per tile, 4 = no MMA, 2 = no staging / store
   int base_offset_mode;  // experiment switch, default 0: MEASURED on B200 -- a SW128 tile whose start is shifted by
                          // q*128 B is addressed correctly with base-offset 0 (the XOR uses absolute address bits);
                          // writing q into bits 49..51 gives wrong results
@@ -93,6 +95,12 @@ dw_tma_kernel(const __grid_constant__ Params p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x;
+  const int tw = (blockIdx.x == 0 && blockIdx.y == 0) ? 0 : -1;
+  if (tid == 0) {
+    trace_head(p.trace, tw, 3);
+    trace_stamp(p.trace, tw, 1);
+    trace_cta(p.trace, p.dbg, blockIdx.y * gridDim.x + blockIdx.x, 0);
+  }
   const int tile0 = blockIdx.y * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.tiles_per_chan - tile0);
   // n-th tile of this CTA; reversed walks start at the last utterances (CTAs with a low blockIdx.y are scheduled first)
@@ -127,18 +135,22 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(p.trace, tw, 2);
 
   pdl_launch_dependents();   // the next kernel may begin its prologue once every CTA of this grid is here
   if (warp == 0) {
     // ===== TMA producer (starts streaming immediately; the Toeplitz build overlaps) =====
     if (lane == 0) {
       pdl_wait();              // first read of the previous kernel's output
+      trace_stamp(p.trace, tw, 3);
+      long long w12 = 0;
       for (int n = 0; n < ntiles; ++n) {
         const int s = n % NSTAGE;
-        ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1);
+        TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w12, ptx::mbar_wait(&empty_bar[s], ((n / NSTAGE) & 1) ^ 1));
         ptx::mbar_arrive_expect_tx(&full_bar[s], box_bytes);
         tma_load_4d(sA + s * A_STAGE, &p.in, &full_bar[s], 0, -p.HL, c, tile_at(n) * p.NB);
       }
+      trace_put(p.trace, tw, 12, w12);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -146,12 +158,15 @@ dw_tma_kernel(const __grid_constant__ Params p) {
       const uint32_t idesc = ptx::umma_idesc_16(MROWS, L, 0, 0, p.f16);
       const uint32_t sb = ptx::smem_u32(sB);
       const int jlo = 64 * p.HL - p.P, jhi = 64 * p.HL + 63 + p.P;  // non-zero band of the stacked Toeplitz rows
+      long long w10 = 0, w11 = 0;
+      const long long t_loop0 = trace_clock();
       ptx::mbar_wait(b_ready, 0);
       for (int n = 0; n < ntiles; ++n) {
         const int s = n % NSTAGE, a = n % ACC_STAGES;
-        ptx::mbar_wait(&acc_empty[a], ((n / ACC_STAGES) & 1) ^ 1);
-        ptx::mbar_wait(&full_bar[s], (n / NSTAGE) & 1);
+        TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w11, ptx::mbar_wait(&acc_empty[a], ((n / ACC_STAGES) & 1) ^ 1));
+        TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w10, ptx::mbar_wait(&full_bar[s], (n / NSTAGE) & 1));
         ptx::tc_fence_after();
+        if (n == 0) trace_stamp(p.trace, tw, 4);
         const uint32_t sa = ptx::smem_u32(sA + s * A_STAGE);
         uint32_t acc = 0;
 #pragma unroll
@@ -170,6 +185,9 @@ dw_tma_kernel(const __grid_constant__ Params p) {
         ptx::mma_commit(&empty_bar[s]);
         ptx::mma_commit(&acc_full[a]);
       }
+      trace_put(p.trace, tw, 10, w10);
+      trace_put(p.trace, tw, 11, w11);
+      trace_put(p.trace, tw, 15, trace_clock() - t_loop0);
     }
   }
   if (warp >= 2) {
@@ -210,14 +228,16 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     const int t = 64 * i;
     const uint32_t srow = ptx::smem_u32(sO) + row * 128;
     pdl_wait();                // no global write of this grid may overtake the previous grid's reads
+    long long w13 = 0, w14 = 0;
     for (int n = 0; n < ntiles; ++n) {
       const int a = n % ACC_STAGES;
       const int b0 = tile_at(n) * p.NB;
       const int b = b0 + bl;
       int lout = p.T;
       if (p.lens && bl < p.NB && b < p.B) lout = min(lout, max(__ldg(p.lens + b), 0));
-      ptx::mbar_wait(&acc_full[a], (n / ACC_STAGES) & 1);
+      TS_TIMED_WAIT((p.trace != nullptr && tw == 0 && tid == 128), w13, ptx::mbar_wait(&acc_full[a], (n / ACC_STAGES) & 1));
       ptx::tc_fence_after();
+      if (n == 0 && tid == 128) trace_stamp(p.trace, tw, 6);
       uint32_t v[64];
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * L);
       ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -226,7 +246,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[a]);
       // the previous tile's TMA store must have finished READING the staging buffer
-      if (tid == 128) bulk_wait_read0();
+      if (tid == 128) TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w14, bulk_wait_read0());
       named_bar_sync(1, 128);
       const bool interior = t + 64 <= lout;
       auto pack_and_stage = [&](auto f16_tag) {   // uniform branch on the row format: one conversion per pair on each path
@@ -260,13 +280,23 @@ dw_tma_kernel(const __grid_constant__ Params p) {
         bulk_commit();
       }
     }
-    if (tid == 128) bulk_wait0();
+    if (tid == 128) {
+      trace_stamp(p.trace, tw, 7);
+      trace_put(p.trace, tw, 13, w13);
+      trace_put(p.trace, tw, 14, w14);
+      bulk_wait0();
+      trace_stamp(p.trace, tw, 8);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (tid == 0) {
+    trace_stamp(p.trace, tw, 9);
+    trace_cta(p.trace, p.dbg, blockIdx.y * gridDim.x + blockIdx.x, 1);
   }
 }
 
@@ -318,6 +348,7 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
   }
   const int groups = ceil_div(p.tiles_per_chan, p.tiles_per_cta);
   p.base_offset_mode = option_dw_base_offset();
+  p.dbg = option_dbg();
   int rc;
   cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[3] = {128, (cuuint64_t)pitch_in * 2, (cuuint64_t)C * pitch_in * 2};
@@ -333,6 +364,7 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
     attr_set = true;
   }
   dim3 grid(C, groups);
+  p.trace = trace_next_slot(3, (unsigned)(C * groups));
   if (p.NQ <= 3)
     TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<3>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ), st, option_pdl() != 0, p));
   else

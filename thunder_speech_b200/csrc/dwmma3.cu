@@ -23,7 +23,9 @@ namespace dwt3 {
 constexpr int L = 64;
 constexpr int MROWS = 128;
 constexpr int A_STAGE = 17 * 1024;     // 132 rows x 128 B rounded up to a multiple of 1024
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 2;               // input stages per CTA at 2 CTAs / SM
+constexpr int SMALL_NSTAGE = 3;         // ... at 1 CTA / SM ("small footprint" mode, see launch_dw_persist)
+constexpr int MAX_NSTAGE = 3;
 constexpr int BQ = 64 * 128;           // one Toeplitz block: 64 rows (r) x 64 k (j) 16-bit = 8 KB
 constexpr int MAX_NQ = 5;
 constexpr int OUT_STAGE = MROWS * 128; // 16 KB
@@ -32,8 +34,8 @@ constexpr int TMEM_COLS = ACC_STAGES * L;  // 256
 constexpr int THREADS = 256;
 constexpr int BUILDERS = 64;
 constexpr int WP_FLOATS = 64 * MAX_NQ + 80;   // zero-padded dilated tap line
-__host__ __device__ constexpr int smem_bytes(int nq, int nbuf) {
-  return NSTAGE * A_STAGE + nbuf * nq * BQ + OUT_STAGE + WP_FLOATS * 4 + 256 + 1024;
+__host__ __device__ constexpr int smem_bytes(int nq, int nbuf, int nstage) {
+  return nstage * A_STAGE + nbuf * nq * BQ + OUT_STAGE + WP_FLOATS * 4 + 256 + 1024;
 }
 
 struct Params {
@@ -43,10 +45,12 @@ struct Params {
   int B, C, T, K, P, D;
   int W, R, NB;
   int HL, NQ, nbuf;      // left halo windows; Toeplitz blocks; Toeplitz buffers (2, or 1 when two sets do not fit)
+  int nstage;            // input stages (NSTAGE, or SMALL_NSTAGE with one CTA per SM)
   int tiles_per_chan;
   long long total;       // C * tiles_per_chan work items, channel-major
   int f16;
   int rev;
+  unsigned long long* trace;   // ts_trace slot of this launch (nullptr: off)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -87,18 +91,24 @@ dw_persist_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
+  const int NSTAGE = p.nstage;          // shadows the namespace constant: stage count of THIS launch
   uint8_t* sB = sA + NSTAGE * A_STAGE;
   uint8_t* sO = sB + p.nbuf * p.NQ * BQ;
   float* wp = reinterpret_cast<float*>(sO + OUT_STAGE);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(wp + WP_FLOATS);
-  uint64_t* empty_bar = full_bar + NSTAGE;
-  uint64_t* acc_full = empty_bar + NSTAGE;
+  uint64_t* empty_bar = full_bar + MAX_NSTAGE;
+  uint64_t* acc_full = empty_bar + MAX_NSTAGE;
   uint64_t* acc_empty = acc_full + ACC_STAGES;
   uint64_t* b_ready = acc_empty + ACC_STAGES;
   uint64_t* b_free = b_ready + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tw = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1);
+  if (tid == 0) {
+    trace_head(p.trace, tw, 2);
+    trace_stamp(p.trace, tw, 1);
+  }
   // contiguous balanced share of the channel-major work list
   const long long g0 = p.total * blockIdx.x / gridDim.x, g1 = p.total * (blockIdx.x + 1) / gridDim.x;
   const int ntiles = (int)(g1 - g0);
@@ -141,12 +151,14 @@ dw_persist_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace_stamp(p.trace, tw, 2);
 
   pdl_launch_dependents();   // the next kernel may begin its prologue once every CTA of this grid is here
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       pdl_wait();              // first read of the previous kernel's output
+      trace_stamp(p.trace, tw, 3);
       for (int n = 0; n < ntiles; ++n) {
         int c, tl;
         item(n, c, tl);
@@ -177,6 +189,7 @@ dw_persist_kernel(const __grid_constant__ Params p) {
         ptx::mbar_wait(&acc_empty[a], ((n / ACC_STAGES) & 1) ^ 1);
         ptx::mbar_wait(&full_bar[s], (n / NSTAGE) & 1);
         ptx::tc_fence_after();
+        if (n == 0) trace_stamp(p.trace, tw, 4);
         const uint32_t sa = ptx::smem_u32(sA + s * A_STAGE);
         uint32_t acc = 0;
 #pragma unroll
@@ -194,6 +207,7 @@ dw_persist_kernel(const __grid_constant__ Params p) {
         ptx::mma_commit(&empty_bar[s]);
         ptx::mma_commit(&acc_full[a]);
       }
+      trace_stamp(p.trace, tw, 5);
     }
   } else {
     // ===== Toeplitz builders: Tq[r][jj] = wline[64 q + jj - 64 HL - r + P], SW128 rows of 128 B =====
@@ -257,6 +271,7 @@ dw_persist_kernel(const __grid_constant__ Params p) {
       if (p.lens && bl < p.NB && b < p.B) lout = min(lout, max(__ldg(p.lens + b), 0));
       ptx::mbar_wait(&acc_full[a], (n / ACC_STAGES) & 1);
       ptx::tc_fence_after();
+      if (n == 0 && tid == 128) trace_stamp(p.trace, tw, 6);
       uint32_t v[64];
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * L);
       ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -299,7 +314,11 @@ dw_persist_kernel(const __grid_constant__ Params p) {
         bulk_commit();
       }
     }
-    if (tid == 128) bulk_wait0();
+    if (tid == 128) {
+      trace_stamp(p.trace, tw, 7);
+      bulk_wait0();
+      trace_stamp(p.trace, tw, 8);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -307,11 +326,15 @@ dw_persist_kernel(const __grid_constant__ Params p) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (tid == 0) trace_stamp(p.trace, tw, 9);
 }
 
 }  // namespace dwt3
 
 int option_dw_share_halo();
+int small_footprint(long long frames);
+int option_dwp_nbuf();
+int option_dwp_nstage();
 
 int launch_dw_persist(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                       const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16) {
@@ -336,6 +359,7 @@ int launch_dw_persist(const __nv_bfloat16* x, int B, int C, int T, int pitch_in,
   p.tiles_per_chan = ceil_div(B, p.NB);
   p.total = (long long)C * p.tiles_per_chan;
   p.nbuf = (p.NQ <= 3) ? 2 : 1;     // two Toeplitz sets of 5 blocks would leave room for one CTA per SM only
+  if (option_dwp_nbuf() > 0 && p.NQ <= 3) p.nbuf = option_dwp_nbuf() >= 2 ? 2 : 1;
   int rc;
   cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[3] = {128, (cuuint64_t)pitch_in * 2, (cuuint64_t)C * pitch_in * 2};
@@ -348,14 +372,25 @@ int launch_dw_persist(const __nv_bfloat16* x, int B, int C, int T, int pitch_in,
     TS_CUDA(cudaGetDevice(&dev));
     TS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     TS_CUDA(cudaFuncSetAttribute(dwt3::dw_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dwt3::smem_bytes(3, 2)));
+                                 dwt3::smem_bytes(3, 2, dwt3::MAX_NSTAGE)));
     TS_CUDA(cudaFuncSetAttribute(dwt3::dw_persist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dwt3::smem_bytes(dwt3::MAX_NQ, 1)));
+                                 dwt3::smem_bytes(dwt3::MAX_NQ, 1, dwt3::MAX_NSTAGE)));
   }
   p.rev = next_walk_reversed();
-  long long grid = 2ll * num_sms;
+  // Small-footprint mode (few tiles per CTA): ONE CTA per SM with three input stages (117 KB, 256 TMEM columns), the
+  // counterpart of the slim pair GEMM (pwgemm3.cu): a Toeplitz CTA and a GEMM CTA fit on an SM together, so every launch
+  // of the dw -> pw -> dw chain is resident -- prologue done, first Toeplitz blocks built -- while its predecessor still
+  // computes, and starts streaming the moment the dependency resolves.
+  const bool small = p.NQ <= 3 && small_footprint((long long)B * pitch_in) != 0;
+  p.nstage = small ? dwt3::SMALL_NSTAGE : dwt3::NSTAGE;
+  if (option_dwp_nstage() > 0 && !small) {   // experiment: as many stages as two CTAs per SM allow
+    p.nstage = option_dwp_nstage() > dwt3::MAX_NSTAGE ? dwt3::MAX_NSTAGE : option_dwp_nstage();
+    while (p.nstage > 2 && 2 * (dwt3::smem_bytes(p.NQ, p.nbuf, p.nstage) + 1024) > 232448) --p.nstage;
+  }
+  long long grid = (small ? 1ll : 2ll) * num_sms;
   if (grid > p.total) grid = p.total;
-  const int smem = dwt3::smem_bytes(p.NQ, p.nbuf);
+  const int smem = dwt3::smem_bytes(p.NQ, p.nbuf, p.nstage);
+  p.trace = trace_next_slot(2, (unsigned)grid);
   if (p.NQ <= 3)
     TS_CUDA(launch_pdl(dwt3::dw_persist_kernel<3>, dim3((unsigned)grid), dim3(dwt3::THREADS), smem, st, option_pdl() != 0, p));
   else

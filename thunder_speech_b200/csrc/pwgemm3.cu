@@ -18,19 +18,20 @@
 namespace ts {
 namespace pw3 {
 
-constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;   // tile of the CTA PAIR
+constexpr int BM = 256, BK = 64, UMMA_K = 16;  // tile of the CTA PAIR: 256 (Cout) x BN (frames), BN = 256 or 128 (template)
 constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 weight rows: 16 KB
-constexpr int B_BYTES = BK * (BN / 2) * 2;     // this CTA's half of the activation tile: 16 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGES = 6;                      // streaming mode: 6 stages of (A rows + B half) = 32 KB
+constexpr int STAGES = 6;                      // streaming mode, BN = 256: 6 stages of (A rows + B half) = 32 KB
+constexpr int SMALL_STAGES = 3;                // BN = 128 ("small footprint", see launch_pw_gemm_pair): 3 stages of 24 KB
 constexpr int UNITS = 12;                      // 16 KB units next to the epilogue staging: resident A chunks + B-only stages
 constexpr int MAX_STAGES = 12;
 constexpr int ACC = 2;
-constexpr int EPI_WARPS = 8;
 constexpr int STG_BYTES = 32 * 128;
-constexpr int THREADS = 384;
-constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 + 1024;
+// every epilogue warp owns 32 output channels x BN / (EW / 4) frames of a tile (EW = epilogue warps, 4 per column block)
+__host__ __device__ constexpr int threads(int ew) { return 128 + 32 * ew; }
+__host__ __device__ constexpr int b_bytes(int bn) { return BK * (bn / 2) * 2; }   // this CTA's half of the activation tile
+__host__ __device__ constexpr int smem_bytes(int bn, int ew, int nst) {
+  return nst * (A_BYTES + b_bytes(bn)) + ew * STG_BYTES + 256 + 1024;
+}
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 struct Params {
@@ -53,6 +54,7 @@ struct Params {
   int nst;            // ring stages (6 x 32 KB streaming, 12 - res_kc x 16 KB weight-stationary)
   int rev;            // walk the (utterance, frame-tile) space from the far end (see next_walk_reversed())
   int dbg;            // timing experiment: 32 = the epilogue only drains TMEM (no math, no stores)
+  unsigned long long* trace;   // ts_trace slot of this launch (nullptr: off)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -130,11 +132,22 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// <256, 8>  the streaming kernel;
+// <128, 4>  the small-footprint variant: 256 threads at <= 128 registers (half the register file), 256 TMEM columns.
+// (<128, 8> -- finer tiles with all resources for launches with only 1-3 tiles per pair -- was measured and removed:
+//  QuartzNet at 16 / 32 / 64 utterances 1.79 / 2.33 / 3.61 -> 1.93 / 2.72 / 3.72 ms.  A 256 x 128 tile re-reads the 256
+//  weight rows for half the columns, and at these sizes the kernel is bound by operand bytes per SM, not by tile quanta.)
+template <int BN, int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads(EPI_WARPS), EPI_WARPS == 8 ? 1 : 2)
 pw_gemm_pair_kernel(const __grid_constant__ Params p) {
+  constexpr int CW = BN / (EPI_WARPS / 4);   // frames per epilogue warp: 128 or 64
+  constexpr int B_BYTES = b_bytes(BN);
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = ACC * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;    // == UNITS * 16 KB: [resident A chunks | ring] then the staging tiles
+  // [resident A chunks | ring] then the staging tiles (BN = 256: 6 x 32 KB == UNITS x 16 KB in either mode)
+  uint8_t* stg_base = smem + (BN == 256 ? STAGES * STAGE_BYTES : p.nst * STAGE_BYTES);   // 1024-aligned either way
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
@@ -149,6 +162,12 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.kc0 + p.kc1;
   const uint32_t rank = cluster_ctarank();     // 0 = leader
+  const int tw = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 2 ? 1 : -1);   // traced CTAs: leaders of the first / last pair
+  if (threadIdx.x == 0) {
+    trace_head(p.trace, tw, 1);
+    trace_stamp(p.trace, tw, 1);
+    trace_cta(p.trace, p.dbg, blockIdx.x, 0);
+  }
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   // i-th tile of this pair -> (m-tile, frame tile, utterance).  Streaming: tiles are dealt round-robin.  Weight-stationary:
   // pair p owns m-tile p % m_tiles and strides over the (frame tile, utterance) space with the pairs that share it.
@@ -203,14 +222,17 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
   cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(p.trace, tw, 2);
   // PDL: everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; from here on we
   // read its output.  Let the next kernel start its own prologue as soon as all our CTAs got this far.
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_stamp(p.trace, tw, 3);
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: runs ahead over this CTA's whole tile list =====
     uint32_t cnt = 0;
+    long long w12 = 0;
     int mt, nt, b;
     if (resident && tile_at(0, mt, nt, b)) {   // the weights of this pair's m-tile: loaded ONCE, all k-chunks
       const int m0 = mt * BM + 128 * (int)rank;
@@ -228,7 +250,7 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
       const int t0 = nt * BN + (BN / 2) * (int)rank;     // this CTA's half of the frame tile
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
         const int s = cnt % nst;
-        ptx::mbar_wait(&empty_bar[s], ((cnt / nst) & 1) ^ 1);
+        TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w12, ptx::mbar_wait(&empty_bar[s], ((cnt / nst) & 1) ^ 1));
         uint8_t* sa = ring + s * ring_stage;
         uint8_t* sb = resident ? sa : sa + A_BYTES;
         if (rank == 0)
@@ -241,27 +263,31 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
         const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
         if (!resident) tma2_load_2d(sa, ma, &full_bar[s], k0, m0);       // [128 rows x 64 k]
 #pragma unroll
-        for (int j = 0; j < BN / 128; ++j)
+        for (int j = 0; j < BN / 128; ++j)     // 64-frame boxes of this CTA's half of the frame tile
           tma2_load_3d(sb + j * (BK * 128), mb, &full_bar[s], t0 + 64 * j, k0, b);
       }
     }
+    trace_put(p.trace, tw, 12, w12);
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ===== MMA issuer (leader CTA only) =====
     const uint32_t idesc = ptx::umma_idesc_16(256, BN, 0, 1, p.f16);
     uint32_t cnt = 0;
     int mt, nt, b;
+    long long w10 = 0, w11 = 0;
+    const long long t_loop0 = trace_clock();     // whole life of the issue loop = denominator of the stall shares
     if (resident && tile_at(0, mt, nt, b)) {
       ptx::mbar_wait(a_full, 0);
       ptx::tc_fence_after();
     }
     for (int it = 0; tile_at(it, mt, nt, b); ++it) {
       const int a = it % ACC;
-      ptx::mbar_wait(&tmem_empty[a], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
+      TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w11, ptx::mbar_wait(&tmem_empty[a], ((it / ACC) & 1) ^ 1));   // epilogue has drained this accumulator set
       ptx::tc_fence_after();
       for (int kc = 0; kc < num_k; ++kc, ++cnt) {
         const int s = cnt % nst;
-        ptx::mbar_wait(&full_bar[s], (cnt / nst) & 1);
+        TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w10, ptx::mbar_wait(&full_bar[s], (cnt / nst) & 1));
         ptx::tc_fence_after();
+        if (cnt == 0) trace_stamp(p.trace, tw, 4);
         const uint32_t st = ptx::smem_u32(ring + s * ring_stage);
         const uint32_t sa = resident ? ptx::smem_u32(smem + kc * A_BYTES) : st;
         const uint32_t sb = resident ? st : st + A_BYTES;
@@ -275,16 +301,21 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
       }
       mma2_commit_mcast(&tmem_full[a]);
     }
+    trace_stamp(p.trace, tw, 5);
+    trace_put(p.trace, tw, 10, w10);
+    trace_put(p.trace, tw, 11, w11);
+    trace_put(p.trace, tw, 15, trace_clock() - t_loop0);
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int e = warp - 4;
     const int q = warp & 3;          // TMEM lane quarter accessible to this warp
-    const int h = e >> 2;            // column half [128 h, 128 h + 128) of the 256-frame tile handled by this warp
+    const int h = e >> 2;            // column block [CW h, CW (h + 1)) of the tile handled by this warp
     uint8_t* stg = stg_base + e * STG_BYTES;
     const uint32_t stg_row = ptx::smem_u32(stg) + lane * 128;
+    long long w13 = 0, w14 = 0;
     int mt, nt, b;
     for (uint32_t it = 0; tile_at((int)it, mt, nt, b); ++it) {
-      const int t0 = nt * BN + h * 128;
+      const int t0 = nt * BN + h * CW;
       const int mrow0 = mt * BM + (int)rank * 128 + q * 32;
       const int m = mrow0 + lane;
       const bool m_ok = m < p.Cout;
@@ -294,17 +325,18 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
       float pooled = 0.f;
       float st_s = 0.f, st_ss = 0.f;
       const int a = it % ACC;
-      ptx::mbar_wait(&tmem_full[a], (it / ACC) & 1);
+      TS_TIMED_WAIT((p.trace != nullptr && tw == 0 && threadIdx.x == 128), w13, ptx::mbar_wait(&tmem_full[a], (it / ACC) & 1));
       ptx::tc_fence_after();
+      if (it == 0 && threadIdx.x == 128) trace_stamp(p.trace, tw, 6);
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < CW / 64; ++cc) {
         uint32_t v[64];
         __syncwarp();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * 128 + cc * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * CW + cc * 64);
         ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         ptx::tmem_ld_wait();
-        if (cc == 1) {  // this thread's part of the accumulator is read: tell the leader's MMA warp
+        if (cc == CW / 64 - 1) {  // this thread's part of the accumulator is read: tell the leader's MMA warp
           ptx::tc_fence_before();
           if (rank == 0)
             ptx::mbar_arrive(&tmem_empty[a]);
@@ -334,15 +366,18 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
               }
             }
           }
-          if (lane == 0) bulk_wait_read0();   // previous TMA store has finished reading the staging tile
-          __syncwarp();
           if (tb + 64 > len) {   // block crosses the utterance end (warp-uniform): zero the tail
 #pragma unroll
             for (int j = 0; j < 64; ++j)
               if (tb + j >= len) r[j] = 0.f;
           }
+          if (lane == 0) TS_TIMED_WAIT((p.trace != nullptr && tw == 0 && threadIdx.x == 128), w14, bulk_wait_read0());   // previous TMA store has finished reading the staging tile
+          __syncwarp();
           // (uniform branches on row format / activation so that each path carries exactly one conversion per pair; the
           // ReLU rides in the conversion instruction: F2FP.RELU)
+          // Tried and rejected (round 2): storing each thread's 128-byte output line straight from registers with four
+          // 256-bit stores (STG.256) instead of staging + TMA store.  32 lanes x 32 different lines per instruction is the
+          // worst case for the LSU write path: 512 -> 1024 at 256 x 751 frames 172 -> 222 us, 512 x 512 96 -> 108 us.
           auto pack_and_stage = [&](auto f16_tag, auto relu_tag) {
             constexpr bool kF16 = decltype(f16_tag)::value, kRelu = decltype(relu_tag)::value;
 #pragma unroll
@@ -381,11 +416,17 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
         }
       }
       if (p.pool && m_ok) se_pool_add(p.pool + (size_t)b * p.Cout + m, pooled);
-      if (p.stats && m_ok)   // one slot per (row, 128-frame block): written exactly once, no atomics (deterministic)
+      if (BN == 256 && EPI_WARPS == 8 && p.stats && m_ok)   // one slot per (row, 128-frame block): written exactly once, no atomics (deterministic)
         *reinterpret_cast<float2*>(p.stats + ((((size_t)b * p.Cout + m) * (2 * p.n_tiles)) + nt * 2 + h) * 2) =
             make_float2(st_s, st_ss);
     }
+    if (threadIdx.x == 128) {
+      trace_stamp(p.trace, tw, 7);
+      trace_put(p.trace, tw, 13, w13);
+      trace_put(p.trace, tw, 14, w14);
+    }
     if (lane == 0) bulk_wait0();   // all stores of this warp are complete before the CTA exits
+    if (threadIdx.x == 128) trace_stamp(p.trace, tw, 8);
   }
   ptx::tc_fence_before();
   cluster_sync_all();   // the peer's shared memory / TMEM stay alive until both CTAs are done
@@ -393,11 +434,16 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
     ptx::tc_fence_after();
     tmem2_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) {
+    trace_stamp(p.trace, tw, 9);
+    trace_cta(p.trace, p.dbg, blockIdx.x, 1);
+  }
 }
 
 }  // namespace pw3
 
 int option_pw_resident();
+int small_footprint(long long frames);
 
 // bf16-row outputs with Cout > 128 on CTA pairs; TS_ERR_UNSUPPORTED otherwise (caller falls back)
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
@@ -423,9 +469,17 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   if ((rc = tma::make_3d_bf16(&p.out, out, out_pitch, Cout, B, (uint64_t)out_pitch * 2, (uint64_t)Cout * out_pitch * 2,
                               64, 32, 1)) != TS_OK)
     return rc;
+  // Small-footprint mode (option small, off by default): 256 x 128 tiles, 3 stages of 24 KB, 4 epilogue warps and 256 TMEM
+  // columns -- 89 KB of shared memory, half of the registers and of the tensor memory, so that the CTAs of this launch
+  // are RESIDENT next to the (equally slimmed) Toeplitz CTAs of the previous launch and run their prologue under its tail.
+  // Measured on B200 (tools/ab_small.sh): the overlap is real (tools/trace_chain.py: entry 2.5 us BEFORE the predecessor
+  // ends instead of 2.5 us after) but with half the shared memory each kernel has half the bytes in flight: QuartzNet at
+  // 32 utterances 2.30 -> 3.27 ms, at 256 11.2 -> 19.2 ms.  Kept as an A/B knob.
+  const bool small = stats == nullptr && small_footprint((long long)B * out_pitch) != 0;
+  const int BN = small ? 128 : 256;
   p.Cout = Cout; p.T = T; p.B = B;
   p.m_tiles = ceil_div(Cout, pw3::BM);
-  p.n_tiles = ceil_div(out_pitch, pw3::BN);
+  p.n_tiles = ceil_div(out_pitch, BN);
   p.num_tiles = p.m_tiles * p.n_tiles * B;
   p.shift = shift; p.lens = lens; p.out_pitch = out_pitch; p.relu = relu;
   p.stats = stats;
@@ -438,20 +492,28 @@ int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, 
   // 256 x 751 frames) 90.2 -> 99.4 us, tensor pipe 64 -> 56 % busy, L2 throughput 43 -> 30 % of peak -- the kernel is bound
   // by bytes in flight, not by L2 bandwidth, so the 6 x 32 KB ring stays the default.
   const int kc_total = p.kc0 + p.kc1;
-  p.res_kc = (option_pw_resident() && kc_total <= pw3::UNITS - 4) ? kc_total : 0;
-  p.nst = p.res_kc ? pw3::UNITS - p.res_kc : pw3::STAGES;
+  p.res_kc = (!small && option_pw_resident() && kc_total <= pw3::UNITS - 4) ? kc_total : 0;
+  p.nst = small ? pw3::SMALL_STAGES : (p.res_kc ? pw3::UNITS - p.res_kc : pw3::STAGES);
   p.pool = pool; p.se_scale = se_scale; p.y1 = reinterpret_cast<const __nv_bfloat16*>(y1); p.y1_pitch = y1_pitch;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     TS_CUDA(cudaGetDevice(&dev));
     TS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    TS_CUDA(cudaFuncSetAttribute(pw3::pw_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pw3::SMEM_BYTES));
+    TS_CUDA(cudaFuncSetAttribute(pw3::pw_gemm_pair_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 pw3::smem_bytes(256, 8, pw3::STAGES)));
+    TS_CUDA(cudaFuncSetAttribute(pw3::pw_gemm_pair_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 pw3::smem_bytes(128, 4, pw3::SMALL_STAGES)));
   }
   int pairs = num_sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  TS_CUDA(launch_pdl(pw3::pw_gemm_pair_kernel, dim3(2 * pairs), dim3(pw3::THREADS), pw3::SMEM_BYTES, st,
-                     option_pdl() != 0, p));
+  p.trace = trace_next_slot(1, 2 * pairs);
+  if (small)
+    TS_CUDA(launch_pdl(pw3::pw_gemm_pair_kernel<128, 4>, dim3(2 * pairs), dim3(pw3::threads(4)),
+                       pw3::smem_bytes(128, 4, pw3::SMALL_STAGES), st, option_pdl() != 0, p));
+  else
+    TS_CUDA(launch_pdl(pw3::pw_gemm_pair_kernel<256, 8>, dim3(2 * pairs), dim3(pw3::threads(8)),
+                       pw3::smem_bytes(256, 8, pw3::STAGES), st, option_pdl() != 0, p));
   TS_LAUNCH_CHECK("pw_gemm_pair_kernel");
   return TS_OK;
 }

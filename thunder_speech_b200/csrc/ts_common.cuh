@@ -89,6 +89,63 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ---- phase tracing (diagnostics; ts_trace; compiled in only with -DTS_TRACE=1: `make trace` -> libthunder_b200_trace.so) ---
+// When a trace buffer is installed, every launch of the hot kernels takes the next 32-word slot; CTA 0 stamps
+// %globaltimer (ns) into words 1..9 and the last CTA into words 17..25 at fixed points of its life (entry, prologue done,
+// predecessor complete, first operands, last MMA issued, first accumulator, last store issued, stores drained, exit);
+// words 10..15 of CTA 0 = cycles its role threads spent waiting (operands, free accumulator, free stage, accumulator
+// ready, staging tile read by the previous TMA store) and the life of the MMA issue loop.
+// Word 0 = kernel id (1 pair GEMM, 2 persistent Toeplitz, 3 per-channel Toeplitz) | grid << 8.  nullptr = tracing off.
+// The production library compiles all of this to nothing (measured cost of the live hooks: 1-3 % on the GEMMs).
+#ifndef TS_TRACE
+#define TS_TRACE 0
+#endif
+unsigned long long* trace_next_slot(int kernel_id, unsigned grid);
+#if TS_TRACE
+__device__ __forceinline__ void trace_head(unsigned long long* slot, int which, int kernel_id) {
+  if (slot != nullptr && which == 0) slot[0] = (unsigned long long)kernel_id | ((unsigned long long)gridDim.x << 8);
+}
+__device__ __forceinline__ void trace_stamp(unsigned long long* slot, int which, int i) {
+  if (slot != nullptr && which >= 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    slot[which * 16 + i] = t;
+  }
+}
+// stall accounting: cycles spent inside a wait are summed in a REGISTER of the waiting thread and written once
+// (trace_put) when its role loop ends -- a global read-modify-write per wait would dominate what it measures
+#define TS_TIMED_WAIT(on, acc, stmt)     \
+  do {                                   \
+    long long _t0 = 0;                   \
+    if (on) _t0 = clock64();             \
+    stmt;                                \
+    if (on) (acc) += clock64() - _t0;    \
+  } while (0)
+// dbg bit 7 (128): every CTA also stamps its entry / exit time into words 32 + 2 * cta (+1) behind the slot (the reader
+// must have allocated 32 + 2 * grid words: single-launch diagnostics only, tools/trace_dw.py)
+__device__ __forceinline__ void trace_cta(unsigned long long* slot, int dbg, int cta, int end) {
+  if (slot != nullptr && (dbg & 128)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    slot[32 + 2 * cta + end] = t;
+  }
+}
+__device__ __forceinline__ void trace_put(unsigned long long* slot, int which, int word, long long v) {
+  if (slot != nullptr && which == 0) slot[word] = (unsigned long long)v;
+}
+__device__ __forceinline__ long long trace_clock() { return clock64(); }
+#else
+__device__ __forceinline__ void trace_head(unsigned long long*, int, int) {}
+__device__ __forceinline__ void trace_stamp(unsigned long long*, int, int) {}
+#define TS_TIMED_WAIT(on, acc, stmt) \
+  do {                               \
+    stmt;                            \
+  } while (0)
+__device__ __forceinline__ void trace_cta(unsigned long long*, int, int, int) {}
+__device__ __forceinline__ void trace_put(unsigned long long*, int, int, long long) {}
+__device__ __forceinline__ long long trace_clock() { return 0; }
+#endif
+
 // ---- device helpers ---------------------------------------------------------------------------
 // SqueezeExcite time-pooling accumulator: partial sums are added as 64-bit FIXED-POINT integers (units of 2^-32), so the
 // result does not depend on the order in which the tiles of an utterance arrive (fp32 atomics do: last-bit differences of

@@ -21,6 +21,9 @@ from . import ops
 
 __all__ = ["CTCModule", "BaseCTCModule"]
 
+#: default number of sub-batch chains per captured inference graph (see CTCModule.graph_chains_for)
+DEFAULT_CHAINS = 1
+
 
 class CTCModule(nn.Module):
     MAX_IN_PLACE_GRAPHS = 8     # captured graphs kept for caller-owned input buffers (oldest evicted first)
@@ -52,6 +55,8 @@ class CTCModule(nn.Module):
         self._pipes: Dict[tuple, "_StreamPipe"] = {}
         self._graph_weights = None      # flat list of the tensors the captured graphs bake in (built lazily)
         self._graph_fingerprint = None
+        #: independent sub-batch CHAINS inside one captured graph (None = chosen from the batch size, see graph_chains_for)
+        self.graph_chains: Optional[int] = None
 
     # -- row format of the inference path ---------------------------------------------------------
     def set_precision(self, precision: Optional[str]) -> "CTCModule":
@@ -165,7 +170,7 @@ class CTCModule(nn.Module):
         copied into the graph's own input buffer; ``in_place=True`` declares ``x`` a persistent device buffer owned by the
         caller (a DMA staging buffer): the graph captured for it reads ``x`` where it lies, one graph per such buffer."""
         self._check_graphs_current()    # stale weights must never be replayed (train / load_state_dict in between)
-        key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None, self._row_dtype())
+        key = (x.shape[0], x.shape[1], x.data_ptr() if in_place else None, self._row_dtype(), self.graph_chains_for(x.shape[0]))
         g = self._graphs.get(key)
         if g is None:
             if in_place:    # a caller that passes a fresh tensor every time must not accumulate graphs (and their memory pools)
@@ -175,6 +180,44 @@ class CTCModule(nn.Module):
             g = _PredictGraph(self, x, in_place)
             self._graphs[key] = g
         return g.replay(x)
+
+    def graph_chains_for(self, batch: int) -> int:
+        """How many independent utterance chains a captured forward of ``batch`` utterances is split into.  Utterances
+        never interact in eval mode, so the graph may run the network over disjoint slices of the batch on parallel
+        branches: while one chain's kernel drains (last tiles, TMA store flush) or sets up (TMEM, barriers, first loads),
+        the other chain's kernel has the SMs -- the per-kernel fixed cost that dominates small batches is overlapped
+        instead of serialised.  ``graph_chains`` (attribute) or THUNDER_B200_CHAINS overrides the choice."""
+        import os
+
+        n = self.graph_chains
+        if n is None and os.environ.get("THUNDER_B200_CHAINS"):
+            n = int(os.environ["THUNDER_B200_CHAINS"])
+        if n is None:
+            n = DEFAULT_CHAINS
+        return max(1, min(int(n), batch))
+
+    @torch.no_grad()
+    def _predict_ids_chained(self, x: Tensor, chains: int) -> Tuple[Tensor, Tensor, Tensor]:
+        """``predict_ids`` over ``chains`` contiguous slices of the batch, each on its own stream (forked from / joined to
+        the current one, so it can be captured into one graph); results concatenated in batch order."""
+        if chains <= 1:
+            return self.predict_ids(x)
+        B = x.shape[0]
+        cur = torch.cuda.current_stream()
+        pool = self.__dict__.setdefault("_chain_streams", [])
+        while len(pool) < chains - 1:
+            pool.append(torch.cuda.Stream(device=x.device))
+        side = pool[:chains - 1]
+        for s in side:      # fork BEFORE chain 0 queues anything on the current stream
+            s.wait_stream(cur)
+        parts = []
+        for i in range(chains):
+            lo, hi = B * i // chains, B * (i + 1) // chains
+            with torch.cuda.stream(cur if i == 0 else side[i - 1]):
+                parts.append(self.predict_ids(x[lo:hi]))
+        for s in side:
+            cur.wait_stream(s)
+        return tuple(torch.cat(p, 0) for p in zip(*parts))
 
     def training_step(self, batch, batch_idx: int = 0) -> Tensor:
         """``BaseCTCModule.training_step`` (src/thunder/module.py:102-127): ``batch = (audio, audio_lengths, texts)`` -> mean
@@ -402,18 +445,19 @@ class _PredictGraph:
         from . import _lib
 
         self.static_in = example if in_place else example.clone()
+        self.chains = module.graph_chains_for(example.shape[0])
         # warm-up on a side stream (sets kernel attributes, builds plans), then capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                module.predict_ids(self.static_in)
+                module._predict_ids_chained(self.static_in, self.chains)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
-            self.static_out = module.predict_ids(self.static_in)
+            self.static_out = module._predict_ids_chained(self.static_in, self.chains)
         self.kernels_per_replay = _lib.launch_count() - n0
         self.replays = 0
 
