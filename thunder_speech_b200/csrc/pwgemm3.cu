@@ -253,18 +253,20 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
         TS_TIMED_WAIT((p.trace != nullptr && tw == 0), w12, ptx::mbar_wait(&empty_bar[s], ((cnt / nst) & 1) ^ 1));
         uint8_t* sa = ring + s * ring_stage;
         uint8_t* sb = resident ? sa : sa + A_BYTES;
+        // dbg 16 / 8 (timing experiments, results wrong): skip the weight (A) / activation (B) loads of every stage
+        const bool skip_a = (p.dbg & 16) != 0, skip_b = (p.dbg & 8) != 0;
         if (rank == 0)
-          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * ring_stage);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * (ring_stage - (skip_a && !resident ? A_BYTES : 0) - (skip_b ? B_BYTES : 0)));
         else
           mbar_arrive_remote(&full_bar[s], 0);
         const bool seg1 = kc >= p.kc0;
         const CUtensorMap* ma = seg1 ? &p.a1 : &p.a0;
         const CUtensorMap* mb = seg1 ? &p.b1 : &p.b0;
         const int k0 = (seg1 ? kc - p.kc0 : kc) * BK;
-        if (!resident) tma2_load_2d(sa, ma, &full_bar[s], k0, m0);       // [128 rows x 64 k]
+        if (!resident && !skip_a) tma2_load_2d(sa, ma, &full_bar[s], k0, m0);       // [128 rows x 64 k]
 #pragma unroll
         for (int j = 0; j < BN / 128; ++j)     // 64-frame boxes of this CTA's half of the frame tile
-          tma2_load_3d(sb + j * (BK * 128), mb, &full_bar[s], t0 + 64 * j, k0, b);
+          if (!skip_b) tma2_load_3d(sb + j * (BK * 128), mb, &full_bar[s], t0 + 64 * j, k0, b);
       }
     }
     trace_put(p.trace, tw, 12, w12);
