@@ -80,6 +80,19 @@ int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemp
               const int32_t* mel_start, const int32_t* mel_count, const int32_t* mel_off,
               const float* mel_w, int nfilt, int nnz,
               float* logmel, void* stream);
+/* ts_logmel with the train()-mode dither of DitherAudio.forward (src/thunder/quartznet/transform.py:109-118) fused in:
+ * every sample becomes x + dither * n, n ~ N(0, 1), BEFORE the pre-emphasis, inside the kernel (no extra pass over the
+ * audio).  n is counter-based (Philox4x32-10 keyed by `seed`, counter = (sample index / 4, utterance), Box-Muller): the
+ * result is a pure function of (audio, seed) -- reproducible, independent of the launch geometry -- but NOT torch's
+ * random stream (the reference draws torch.randn_like), so parity with the reference is statistical.  dither = 0 is
+ * ts_logmel bit for bit.  seed_dev (nullable, DEVICE pointer to one u64) is XORed into `seed` by the kernel: a per-step
+ * state the caller advances on the stream, so that a captured CUDA graph draws fresh noise on every replay. */
+int ts_logmel_dither(const float* audio, int B, int N, int n_fft, int hop, float preemph,
+                     const float* window_full, int win_lo, int win_hi, const float* twiddle,
+                     const int32_t* mel_start, const int32_t* mel_count, const int32_t* mel_off,
+                     const float* mel_w, int nfilt, int nnz,
+                     float* logmel, float dither, unsigned long long seed, const unsigned long long* seed_dev,
+                     void* stream);
 
 /* The same three stages with the STFT as a DFT-MATRIX CONTRACTION on the tensor cores (tcgen05, CTA pairs; the
  * reference's own DFT-matrix STFT is src/thunder/blocks.py:38-91): n_fft = 512 with the window supported on [96, 416)
@@ -178,6 +191,14 @@ int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch,
  * its channel mixing then runs in ts_pw_gemm.  T_out = (T_in - 1) / S + 1 */
 int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_in, int S, const int32_t* len_in, void* y,
                    int pitch_out, void* stream);
+/* im2col over 16-bit rows for NON-separable convolutions with kernel_size > 1 (the reference's QuartznetBlock default
+ * `separable=False`, src/thunder/quartznet/blocks.py:212-219, built at :232-243):
+ *   y[b, c*K + k, t] = x[b, c, t*S + k*D - P]  inside [0, min(T_in, len_in[b])), 0 elsewhere and in [T_out, pitch_out)
+ * after which MaskedConv1d.forward (:158-182) is ONE ts_pw_gemm with Cin*K input channels whose weight is conv.weight
+ * [Cout, Cin, K] viewed as [Cout, Cin*K].  x [B, C, pitch_in], y [B, rows_out >= C*K, pitch_out] (rows beyond C*K are the
+ * caller's: zero them when the GEMM's K extent is padded), either 16-bit row format. */
+int ts_im2col_rows(const void* x, int B, int C, int T_in, int pitch_in, int K, int S, int D, int P,
+                   const int32_t* len_in, void* y, int rows_out, int pitch_out, void* stream);
 
 /* ---- layout / length plumbing at module boundaries ------------------------------------------ */
 /* contiguous [B, C, T] (TS_F32, TS_BF16 or TS_F16) -> 16-bit rows [B, C, pitch] of out_dtype TS_BF16 / TS_F16 (frames

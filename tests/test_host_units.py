@@ -132,8 +132,24 @@ def test_block_plan_folds_batchnorm_exactly():
     assert torch.allclose(sub.shift, bn.bias - bn.running_mean * scale, atol=1e-6)
     qb = QuartznetBlock(8, 8, repeat=2, kernel_size=(3,), stride=(2,), residual=True, separable=True).eval()
     assert build_block_plan(qb).res_stride == 4                               # stride ** repeat (quartznet/blocks.py:301)
+    # non-separable kernel_size > 1 (the block's default): BN-folded [Cout, Cin, K] weight viewed as the [Cout, Cin * K]
+    # operand of one GEMM over im2col rows (channel index c * K + k)
+    fb = QuartznetBlock(8, 12, repeat=1, kernel_size=(11,), separable=False, residual=False).eval()
+    fbn = fb.mconv[1].layer[0]
+    fbn.running_var.uniform_(0.5, 1.5); fbn.weight.data.uniform_(0.5, 1.5); fbn.bias.data.normal_(0, 0.1)
+    fplan = build_block_plan(fb)
+    fs = fplan.subs[0]
+    assert fs.full and fs.dw_w is None and tuple(fs.pw_w.shape) == (12, 8 * 11) and (fs.K, fs.S, fs.P) == (11, 1, 5)
+    assert fplan.in_channels == 8 and fplan.out_channels == 12
+    xin = torch.randn(2, 8, 30)
+    cols = torch.nn.functional.unfold(xin[:, :, None, :], (1, 11), padding=(0, 5))          # [B, Cin * K, T], index c * K + k
+    got = torch.einsum("ok,bkt->bot", fs.pw_w.float(), cols) + fs.shift[None, :, None]
+    ref = fbn(fb.mconv[0].conv(xin))
+    assert (got - ref).abs().max() < 2e-2 * ref.abs().max()
     with pytest.raises(NotImplementedError):
-        build_block_plan(QuartznetBlock(8, 8, repeat=1, kernel_size=(11,), separable=False).eval())
+        bad = QuartznetBlock(8, 8, repeat=1, kernel_size=(3,), separable=False).eval()
+        bad.mconv[0].conv.groups = 2          # grouped but not depthwise: not part of the reference's blocks
+        build_block_plan(bad)
 
 
 def test_greedy_decode_string_rules(golden_decode):

@@ -48,9 +48,9 @@ def test_training_mode_and_unsupported_convs_fail_loudly():
     blk = QuartznetBlock(16, 16, repeat=1, kernel_size=(5,), separable=True).cuda()
     with pytest.raises(NotImplementedError):
         blk(torch.zeros(1, 16, 40).cuda(), torch.tensor([40]).cuda())          # .train() mode
-    full = QuartznetBlock(16, 16, repeat=1, kernel_size=(11,), separable=False).eval().cuda()
-    with pytest.raises(NotImplementedError):
-        full(torch.zeros(1, 16, 40).cuda(), torch.tensor([40]).cuda())
+    full = QuartznetBlock(16, 16, repeat=1, kernel_size=(11,), separable=False).eval().cuda()   # default-constructed block
+    y, yl = full(torch.zeros(1, 16, 40).cuda(), torch.tensor([40]).cuda())                      # runs (im2col + GEMM)
+    assert tuple(y.shape) == (1, 16, 40) and int(yl[0]) == 40
     with pytest.raises(ValueError):                                              # blocks.py:192-193
         QuartznetBlock(8, 8, kernel_size=(3,), stride=(2,), dilation=(2,))
 
@@ -67,6 +67,16 @@ def test_masked_conv_and_se_standalone():
     ref, rl = R.masked_conv1d(xb, lens, w, 1, 2, 1, groups=8)
     assert np.array_equal(yl.cpu().numpy(), rl)
     assert rel_err(y.cpu().numpy(), ref)[0] < 2.0 ** -8
+    # full (non-separable) convolutions stand alone: odd Cin * K (padded GEMM extent), stride, dilation, bias
+    for cin, cout, k, s_, d_, p_ in ((8, 12, 11, 1, 1, 5), (3, 5, 7, 2, 1, 3), (6, 160, 5, 1, 2, 4)):
+        fc = MaskedConv1d(cin, cout, k, stride=s_, dilation=d_, padding=p_, bias=True).eval().cuda()
+        xf = rng.standard_normal((2, cin, 50)).astype(np.float32)
+        yf, yfl = fc(torch.from_numpy(xf).cuda(), torch.from_numpy(lens).cuda())
+        xq = torch.from_numpy(xf).bfloat16().float().numpy()
+        wq = fc.conv.weight.detach().bfloat16().float().cpu().numpy()
+        ref, rl = R.masked_conv1d(xq, lens, wq, s_, p_, d_, bias=fc.conv.bias.detach().cpu().numpy())
+        assert np.array_equal(yfl.cpu().numpy(), rl) and tuple(yf.shape) == ref.shape
+        assert rel_err(yf.cpu().numpy(), ref)[0] < 1e-4, (cin, cout, k)        # fp32 output of bf16-rounded operands
     se = SqueezeExcite(32, 8).eval().cuda()
     xs = rng.standard_normal((3, 32, 41)).astype(np.float32)
     got = se(torch.from_numpy(xs).cuda()).cpu().numpy()

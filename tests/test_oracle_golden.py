@@ -90,6 +90,11 @@ BLOCK_CASES = [
                                    dilation=1, residual=True, separable=True), 2, 91),
     ("cn_stem", "citrinet", dict(in_channels=80, out_channels=256, repeat=1, kernel_size=5, stride=1, dilation=1,
                                  residual=False, separable=True), 2, 33),
+    # non-separable convolutions with kernel_size > 1: QuartznetBlock's DEFAULT (quartznet/blocks.py:232-243)
+    ("qn_full", "quartznet", dict(in_channels=16, out_channels=24, repeat=2, kernel_size=11, stride=1, dilation=1,
+                                  residual=True, separable=False), 2, 61),
+    ("qn_full_stride", "quartznet", dict(in_channels=8, out_channels=16, repeat=1, kernel_size=5, stride=2, dilation=1,
+                                         residual=False, separable=False), 2, 50),
 ]
 
 

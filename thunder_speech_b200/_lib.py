@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libthunder_b200.so")
@@ -41,6 +41,9 @@ SIGNATURES = {
     "ts_trace": (c_int, [c_void_p, c_int]),
     "ts_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ts_logmel_dither": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_uint64,
+                                 c_void_p, c_void_p]),
     "ts_logmel_dft": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "ts_feature_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
@@ -97,6 +100,8 @@ SIGNATURES = {
     "ts_ctc_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float,
                             c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ts_gather_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "ts_im2col_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                               c_int, c_void_p]),
     "ts_pack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ts_unpack_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ts_conv_lengths": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -57,6 +57,40 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- train-mode dither (DitherAudio, src/thunder/quartznet/transform.py:109-118: x + dither * N(0, 1)) ------------------
+// Counter-based noise: the four standard normals of samples [4 g, 4 g + 4) of utterance b are Philox4x32-10(key = seed,
+// counter = (g, b)) pushed through Box-Muller, so a sample gets the same noise from every frame / tile / boundary path
+// that touches it and the result depends only on (seed, b, sample index) -- not on the launch geometry.  The stream is
+// NOT torch's (the reference draws torch.randn_like; parity is statistical by construction).
+__device__ __forceinline__ float4 dither_normal4(unsigned long long seed, uint32_t g, uint32_t b) {
+  uint32_t c0 = g, c1 = b, c2 = 0x5eed5eedu, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // uniforms in (0, 1): 24 random bits + 1/2 ulp
+  const float u0 = ((float)(c0 >> 8) + 0.5f) * 5.9604644775390625e-08f, u1 = ((float)(c1 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  const float u2 = ((float)(c2 >> 8) + 0.5f) * 5.9604644775390625e-08f, u3 = ((float)(c3 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float s0, co0, s1, co1;
+  __sincosf(6.283185307179586f * u1, &s0, &co0);
+  __sincosf(6.283185307179586f * u3, &s1, &co1);
+  return make_float4(r0 * co0, r0 * s0, r1 * co1, r1 * s1);
+}
+__device__ __forceinline__ float dither_normal(unsigned long long seed, int s, int b) {
+  const float4 z = dither_normal4(seed, (uint32_t)s >> 2, (uint32_t)b);
+  const int e = s & 3;
+  return e == 0 ? z.x : e == 1 ? z.y : e == 2 ? z.z : z.w;
+}
+
 // Persistent kernel: each CTA loops over (utterance, 32-frame tile) work items.  The raw audio span of the NEXT item is
 // fetched with cp.async into the other half of a double buffer while the current item is transformed.
 //
@@ -72,8 +106,10 @@ logmel_kernel(const float* __restrict__ audio, int B, int N, int F, int hop, flo
               const float* __restrict__ window_full, const float2* __restrict__ twiddle,
               const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
               const int32_t* __restrict__ mel_off, const float* __restrict__ mel_w, int nfilt, int nnz,
-              float* __restrict__ logmel, int tiles_per_row, int num_items) {
+              float* __restrict__ logmel, int tiles_per_row, int num_items, float dither, unsigned long long seed,
+              const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ __align__(16) float smem[];
+  if (dither != 0.f && seed_dev != nullptr) seed ^= *seed_dev;   // per-step state kept on the device (graph replays)
   const SmemLayout L = smem_layout(hop, nfilt, nnz);
   float2* tw = reinterpret_cast<float2*>(smem + L.tw);
   int* s_mstart = reinterpret_cast<int*>(smem + L.mstart);
@@ -134,7 +170,12 @@ logmel_kernel(const float* __restrict__ audio, int B, int N, int F, int hop, flo
         float v = 0.f;
         if (s > -NFFT / 2 - 1 && s < N + NFFT / 2) {
           const int r = s < 0 ? -s : (s >= N ? 2 * (N - 1) - s : s);  // reflect (torch.stft center=True)
-          v = (r >= 1) ? (x[r] - preemph * x[r - 1]) : x[0];          // y[0] = x[0]
+          if (dither == 0.f) {
+            v = (r >= 1) ? (x[r] - preemph * x[r - 1]) : x[0];          // y[0] = x[0]
+          } else {   // the dithered signal is pre-emphasised: xd[r] = x[r] + dither * n(b, r)
+            const float xr = fmaf(dither, dither_normal(seed, r, b), x[r]);
+            v = (r >= 1) ? (xr - preemph * fmaf(dither, dither_normal(seed, r - 1, b), x[r - 1])) : xr;
+          }
         }
         raw[4 + i] = v;
       }
@@ -157,6 +198,22 @@ logmel_kernel(const float* __restrict__ audio, int B, int N, int F, int hop, flo
     const int b = item / tiles_per_row, f0 = (item - b * tiles_per_row) * FT;
     const float* raw = smem + L.raw + buf * L.raw_stride + 4;
     const float pe = s_boundary[buf] ? 0.f : 1.f;
+    if (dither != 0.f && !s_boundary[buf]) {   // train mode: add the noise to the staged raw samples (interior items; uniform)
+      float* rw = smem + L.raw + buf * L.raw_stride;            // rw[i] <-> signal index s0 - 4 + i, i in [3, span + 4)
+      const int sbase = f0 * hop - NFFT / 2 - 4;
+      if ((sbase & 3) == 0) {                                   // groups of four aligned with the Philox counter
+        for (int i4 = tid; i4 < (span + 8) / 4; i4 += NWARPS * 32) {
+          const float4 z = dither_normal4(seed, (uint32_t)(sbase + 4 * i4) >> 2, (uint32_t)b);
+          float4* q = reinterpret_cast<float4*>(rw) + i4;
+          float4 v = *q;
+          v.x = fmaf(dither, z.x, v.x); v.y = fmaf(dither, z.y, v.y); v.z = fmaf(dither, z.z, v.z); v.w = fmaf(dither, z.w, v.w);
+          *q = v;
+        }
+      } else {
+        for (int i = tid + 3; i < span + 4; i += NWARPS * 32) rw[i] = fmaf(dither, dither_normal(seed, sbase + i, b), rw[i]);
+      }
+      __syncthreads();
+    }
 
     constexpr int PAIRS_PER_WARP = FT / NWARPS / 2;
 #pragma unroll 1
@@ -420,11 +477,12 @@ extern "C" int ts_feature_normalize_partials(const float* logmel, const float* p
   return TS_OK;
 }
 
-extern "C" int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemph,
+static int logmel_launch(const float* audio, int B, int N, int n_fft, int hop, float preemph,
                          const float* window_full, int win_lo, int win_hi, const float* twiddle,
                          const int32_t* mel_start,
                          const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int nfilt,
-                         int nnz, float* logmel, void* stream) {
+                         int nnz, float* logmel, float dither, unsigned long long seed,
+                         const unsigned long long* seed_dev, void* stream) {
   TS_REQUIRE(audio && window_full && twiddle && mel_start && mel_count && mel_off && mel_w && logmel,
              TS_ERR_INVALID, "ts_logmel: null pointer");
   TS_REQUIRE(B > 0 && hop > 0 && nfilt > 0 && nnz > 0, TS_ERR_INVALID, "ts_logmel: bad sizes B=%d hop=%d nfilt=%d", B,
@@ -458,9 +516,27 @@ extern "C" int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, f
   const int grid = num_items < 2 * num_sms ? num_items : 2 * num_sms;
   kern<<<grid, feat::NWARPS * 32, smem, (cudaStream_t)stream>>>(
       audio, B, N, F, hop, preemph, window_full, reinterpret_cast<const float2*>(twiddle), mel_start, mel_count,
-      mel_off, mel_w, nfilt, nnz, logmel, tiles_per_row, num_items);
+      mel_off, mel_w, nfilt, nnz, logmel, tiles_per_row, num_items, dither, seed, seed_dev);
   TS_LAUNCH_CHECK("logmel_kernel");
   return TS_OK;
+}
+
+extern "C" int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemph,
+                         const float* window_full, int win_lo, int win_hi, const float* twiddle,
+                         const int32_t* mel_start,
+                         const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int nfilt,
+                         int nnz, float* logmel, void* stream) {
+  return logmel_launch(audio, B, N, n_fft, hop, preemph, window_full, win_lo, win_hi, twiddle, mel_start, mel_count, mel_off,
+                       mel_w, nfilt, nnz, logmel, 0.f, 0ull, nullptr, stream);
+}
+
+extern "C" int ts_logmel_dither(const float* audio, int B, int N, int n_fft, int hop, float preemph,
+                                const float* window_full, int win_lo, int win_hi, const float* twiddle,
+                                const int32_t* mel_start, const int32_t* mel_count, const int32_t* mel_off,
+                                const float* mel_w, int nfilt, int nnz, float* logmel, float dither,
+                                unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
+  return logmel_launch(audio, B, N, n_fft, hop, preemph, window_full, win_lo, win_hi, twiddle, mel_start, mel_count, mel_off,
+                       mel_w, nfilt, nnz, logmel, dither, seed, seed_dev, stream);
 }
 
 extern "C" int ts_feature_normalize(const float* logmel, const int64_t* lengths, int B, int nfilt, int F, int hop,

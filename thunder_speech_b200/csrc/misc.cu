@@ -138,6 +138,38 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int C, i
   *reinterpret_cast<uint4*>(y + row * pitch_out + t0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// im2col over 16-bit rows: y[b, c * K + k, t] = x[b, c, t * S + k * D - P] inside [0, min(T_in, len_in[b])), else 0; zero in
+// [T_out, pitch_out).  Turns a NON-separable MaskedConv1d with kernel_size > 1 (the reference's QuartznetBlock default,
+// src/thunder/quartznet/blocks.py:212-219) into ONE pointwise GEMM with Cin * K input channels on the pair-GEMM kernel --
+// conv.weight [Cout, Cin, K] is that GEMM's [Cout, Cin * K] weight as it lies in memory.  8 frames per thread.
+__global__ void im2col_rows_kernel(const unsigned short* __restrict__ x, int C, int T_in, int pitch_in, int K, int S, int D,
+                                   int P, const int32_t* __restrict__ len_in, unsigned short* __restrict__ y, int T_out,
+                                   int pitch_out, long long rows, int rows_out) {
+  const long long row = blockIdx.x;            // (b, c, k)
+  const int t0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (row >= rows || t0 >= pitch_out) return;
+  const int k = (int)(row % K);
+  const long long bc = row / K;
+  int lin = T_in;
+  if (len_in != nullptr) lin = min(lin, max(len_in[bc / C], 0));
+  const unsigned short* xr = x + bc * pitch_in;
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    unsigned short v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int t = t0 + 2 * h + e;
+      const int src = t * S + k * D - P;
+      v[e] = (t < T_out && src >= 0 && src < lin) ? xr[src] : (unsigned short)0;
+    }
+    o[h] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+  }
+  // utterance b's rows start at b * rows_out (>= C * K: the GEMM's K extent may be padded by the caller)
+  const long long b = bc / C, ck = row - b * C * K;
+  *reinterpret_cast<uint4*>(y + (b * rows_out + ck) * pitch_out + t0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // SE excite for blocks WITHOUT a residual branch (Citrinet stem / epilogue, citrinet/blocks.py:154,195-197):
 // out = relu(gate[b, c] * y1[b, c, t]), frames t >= lens[b] stored as zero when lens is given.  8 frames per thread.
 __global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ y1, const float* __restrict__ gate, int C, int pitch,
@@ -344,6 +376,26 @@ extern "C" int ts_gather_rows(const void* x, int B, int C, int T_in, int pitch_i
   misc::gather_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, T_in, pitch_in, S, len_in,
                                                                    (__nv_bfloat16*)y, pitch_out, rows);
   TS_LAUNCH_CHECK("gather_rows_kernel");
+  return TS_OK;
+}
+
+extern "C" int ts_im2col_rows(const void* x, int B, int C, int T_in, int pitch_in, int K, int S, int D, int P,
+                              const int32_t* len_in, void* y, int rows_out, int pitch_out, void* stream) {
+  TS_REQUIRE(x && y, TS_ERR_INVALID, "ts_im2col_rows: null pointer");
+  TS_REQUIRE(B > 0 && C > 0 && T_in > 0 && K > 0 && S > 0 && D > 0 && P >= 0 && pitch_in >= T_in && pitch_out % 8 == 0,
+             TS_ERR_INVALID, "ts_im2col_rows: bad sizes");
+  const int T_out = (T_in + 2 * P - D * (K - 1) - 1) / S + 1;
+  TS_REQUIRE(T_in + 2 * P - D * (K - 1) - 1 >= 0 && T_out > 0, TS_ERR_INVALID, "ts_im2col_rows: empty output (T_in=%d K=%d)",
+             T_in, K);
+  TS_REQUIRE(pitch_out >= T_out, TS_ERR_INVALID, "ts_im2col_rows: pitch_out %d < T_out %d", pitch_out, T_out);
+  TS_REQUIRE(rows_out >= C * K, TS_ERR_INVALID, "ts_im2col_rows: rows_out %d < C * K = %d", rows_out, C * K);
+  const long long rows = (long long)B * C * K;
+  TS_REQUIRE(rows < (1ll << 31), TS_ERR_UNSUPPORTED, "ts_im2col_rows: too many rows");
+  dim3 grid((unsigned)rows, ceil_div(pitch_out / 8, 128));
+  misc::im2col_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const unsigned short*)x, C, T_in, pitch_in, K, S, D, P,
+                                                                   len_in, (unsigned short*)y, T_out, pitch_out, rows,
+                                                                   rows_out);
+  TS_LAUNCH_CHECK("im2col_rows_kernel");
   return TS_OK;
 }
 

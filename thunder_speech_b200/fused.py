@@ -37,8 +37,9 @@ class SubPlan:
     S: int
     D: int
     P: int
-    pw_w: Tensor                # [Cout, Cin] bf16, BN scale folded
+    pw_w: Tensor                # [Cout, Cin] bf16, BN scale folded ([Cout, Cin * K] for a full convolution)
     shift: Tensor               # [Cout] f32
+    full: bool = False          # non-separable conv with kernel_size > 1: im2col rows + one GEMM over Cin * K channels
 
 
 @dataclass
@@ -77,8 +78,9 @@ def params_key(module: nn.Module):
 
 def build_block_plan(block: nn.Module, dtype: torch.dtype = torch.bfloat16) -> BlockPlan:
     """Reads a block laid out like the reference (``mconv`` = [dw, pw, BN, (ReLU, Dropout)]*, optional SE,
-    ``res`` = [conv1x1, BN]) and folds it into a plan.  Non-separable convs are supported for kernel_size 1
-    (the only non-separable layer of the models, quartznet/blocks.py:399-407)."""
+    ``res`` = [conv1x1, BN]) and folds it into a plan.  Non-separable convs: kernel_size 1 is a plain GEMM (the only
+    non-separable layer of the models, quartznet/blocks.py:399-407); kernel_size > 1 (the block's DEFAULT, :232-243) runs as
+    im2col rows + one GEMM over ``Cin * K`` channels."""
     from .quartznet.blocks import MaskedConv1d  # local import: blocks.py imports this module
 
     plan = BlockPlan()
@@ -94,11 +96,24 @@ def build_block_plan(block: nn.Module, dtype: torch.dtype = torch.bfloat16) -> B
             else:
                 dwl, (pwl,) = None, pending
             conv = pwl.conv
-            if conv.kernel_size[0] != 1 or conv.stride[0] != 1 or conv.groups != 1:
-                raise NotImplementedError(
-                    "non-separable convolutions are implemented for kernel_size=1, stride=1 only "
-                    f"(got k={conv.kernel_size[0]}, s={conv.stride[0]}); the Quartznet/Citrinet models use "
-                    "separable blocks everywhere else")
+            if conv.groups != 1:
+                raise NotImplementedError(f"grouped non-depthwise convolutions are not implemented (groups={conv.groups})")
+            if dwl is None and (conv.kernel_size[0] != 1 or conv.stride[0] != 1):
+                # full convolution (QuartznetBlock's default separable=False, quartznet/blocks.py:212-219): the BN-folded
+                # weight [Cout, Cin, K] IS the [Cout, Cin * K] operand of one GEMM over im2col rows
+                scale, shift = _bn_fold(inner)
+                w = conv.weight.detach().float() * scale[:, None, None]
+                if conv.bias is not None:
+                    shift = shift + conv.bias.detach().float() * scale
+                if dtype == torch.float16:
+                    w = w.clamp(-65504.0, 65504.0)
+                w2 = w.reshape(w.shape[0], -1)
+                if w2.shape[1] % 8:     # whole 16-byte groups along the GEMM's K (matches ops.im2col_rows' zero rows)
+                    w2 = torch.nn.functional.pad(w2, (0, 8 - w2.shape[1] % 8))
+                plan.subs.append(SubPlan(None, pwl.kernel_size, pwl.stride, pwl.dilation, pwl.padding,
+                                         w2.to(dtype).contiguous(), shift.contiguous(), True))
+                pending = []
+                continue
             pw_w, shift = _fold_pw(conv, inner, dtype)
             if dwl is not None:
                 dw_w = dwl.conv.weight.detach().float()[:, 0, :].contiguous()
@@ -118,7 +133,8 @@ def build_block_plan(block: nn.Module, dtype: torch.dtype = torch.bfloat16) -> B
         if plan.res_stride > 1:
             plan.ones = torch.ones((rconv.conv.in_channels, 1), device=plan.res_w.device, dtype=torch.float32)
         plan.total_shift = (plan.subs[-1].shift + plan.res_shift).contiguous()
-    plan.in_channels = plan.subs[0].pw_w.shape[1]
+    first = next(iter(block.mconv.children()))
+    plan.in_channels = first.conv.in_channels
     plan.out_channels = plan.subs[-1].pw_w.shape[0]
     return plan
 
@@ -144,6 +160,10 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
         last = r == n - 1
         if sb.dw_w is not None:
             a = ops.dw_conv(cur, Tc, sb.dw_w, sb.S, sb.D, sb.P, lc, True)  # rows are zero beyond lc
+            Ta = conv_out_length(Tc, sb.K, sb.S, sb.P, sb.D)
+            la = _next_lens(lc, sb.K, sb.S, sb.D, sb.P)
+        elif sb.full:
+            a = ops.im2col_rows(cur, Tc, sb.K, sb.S, sb.D, sb.P, lc)      # [B, Cin * K, pitch'] (input masked by lc)
             Ta = conv_out_length(Tc, sb.K, sb.S, sb.P, sb.D)
             la = _next_lens(lc, sb.K, sb.S, sb.D, sb.P)
         else:
@@ -210,7 +230,7 @@ class PlannedBlock(nn.Module):
         """Lengths after the main branch, computed with the reference's own formula on the caller's tensor
         (dtype preserved, quartznet/blocks.py:142-156)."""
         for sb in self._plan().subs:
-            if sb.dw_w is not None:
+            if sb.dw_w is not None or sb.full:
                 lengths = conv_out_length(lengths, sb.K, sb.S, sb.P, sb.D)
         return lengths
 

@@ -74,8 +74,11 @@ def _f16_flag(t: Tensor) -> int:
 @torch.library.custom_op(f"{NS}::filterbank", mutates_args=())
 def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Tensor, mel_start: Tensor,
                mel_count: Tensor, mel_off: Tensor, mel_w: Tensor, hop: int, preemph: float, win_lo: int,
-               win_hi: int, div_guard: float, out_bf16_pitch: int, out_f16: bool = False) -> Tuple[Tensor, Tensor]:
-    """Eval-mode ``FilterbankFeatures`` (src/thunder/quartznet/transform.py:258-321).
+               win_hi: int, div_guard: float, out_bf16_pitch: int, out_f16: bool = False, dither: float = 0.0,
+               seed: int = 0, seed_state: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``FilterbankFeatures`` (src/thunder/quartznet/transform.py:258-321); ``dither != 0`` adds the train()-mode
+    ``DitherAudio`` noise inside the feature kernel (counter-based normals keyed by ``seed`` XOR the device-resident
+    ``seed_state`` (int64 ``[1]``), which the caller advances per step -- graph replays then draw fresh noise).
 
     ``out_bf16_pitch == 0``: returns ``(features[B,nfilt,F] f32, feature_lengths[B] i64)`` exactly like the
     reference.  ``out_bf16_pitch > 0``: features are emitted as 16-bit padded rows ``[B,nfilt,pitch]`` for the
@@ -91,9 +94,16 @@ def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Ten
     lens64 = lengths.to(torch.int64).contiguous()
     L = _lib.lib()
     logmel = torch.empty((B, nfilt, F), device=audio.device, dtype=torch.float32)
-    _lib.check(L.ts_logmel(_ptr(audio), B, N, n_fft, hop, preemph, _ptr(window_full), win_lo, win_hi,
-                           _ptr(twiddle), _ptr(mel_start), _ptr(mel_count), _ptr(mel_off), _ptr(mel_w), nfilt,
-                           mel_w.numel(), _ptr(logmel), _stream()), "ts_logmel")
+    if dither != 0.0:
+        _lib.check(L.ts_logmel_dither(_ptr(audio), B, N, n_fft, hop, preemph, _ptr(window_full), win_lo, win_hi,
+                                      _ptr(twiddle), _ptr(mel_start), _ptr(mel_count), _ptr(mel_off), _ptr(mel_w), nfilt,
+                                      mel_w.numel(), _ptr(logmel), float(dither), int(seed) & (2 ** 64 - 1),
+                                      _ptr(seed_state) if seed_state is not None else None, _stream()),
+                   "ts_logmel_dither")
+    else:
+        _lib.check(L.ts_logmel(_ptr(audio), B, N, n_fft, hop, preemph, _ptr(window_full), win_lo, win_hi,
+                               _ptr(twiddle), _ptr(mel_start), _ptr(mel_count), _ptr(mel_off), _ptr(mel_w), nfilt,
+                               mel_w.numel(), _ptr(logmel), _stream()), "ts_logmel")
     seq = torch.empty((B,), device=audio.device, dtype=torch.int64)
     if out_bf16_pitch > 0:
         out = torch.empty((B, nfilt, out_bf16_pitch), device=audio.device,
@@ -109,7 +119,7 @@ def filterbank(audio: Tensor, lengths: Tensor, window_full: Tensor, twiddle: Ten
 
 @filterbank.register_fake
 def _(audio, lengths, window_full, twiddle, mel_start, mel_count, mel_off, mel_w, hop, preemph, win_lo, win_hi,
-      div_guard, out_bf16_pitch, out_f16=False):
+      div_guard, out_bf16_pitch, out_f16=False, dither=0.0, seed=0, seed_state=None):
     B, N = audio.shape
     nfilt = mel_start.numel()
     F = 1 + N // hop
@@ -367,6 +377,29 @@ def conv_lengths(lens: Tensor, kernel_size: int, stride: int, dilation: int, pad
 @conv_lengths.register_fake
 def _(lens, kernel_size, stride, dilation, padding):
     return torch.empty_like(lens)
+
+
+@torch.library.custom_op(f"{NS}::im2col_rows", mutates_args=())
+def im2col_rows(x: Tensor, T_in: int, K: int, stride: int, dilation: int, padding: int, lens: Optional[Tensor]) -> Tensor:
+    """``y[b, c*K + k, t] = x[b, c, t*stride + k*dilation - padding]`` (zero outside the utterance / the conv padding) over
+    16-bit rows: the operand that turns a non-separable ``MaskedConv1d`` with ``kernel_size > 1`` into one ``pw_gemm``."""
+    _need_cuda(x)
+    B, C, pitch = x.shape
+    T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
+    CK = (C * K + 7) // 8 * 8          # the GEMM's K extent in whole 16-byte groups (TMA row pitch); extra rows are zero
+    out = torch.empty((B, CK, row_pitch(max(T_out, 1))), device=x.device, dtype=x.dtype)
+    if CK != C * K:
+        out[:, C * K:].zero_()
+    _lib.check(_lib.lib().ts_im2col_rows(_ptr(x), B, C, T_in, pitch, K, stride, dilation, padding,
+                                         _ptr(lens) if lens is not None else None, _ptr(out), CK, out.shape[2], _stream()),
+               "ts_im2col_rows")
+    return out
+
+
+@im2col_rows.register_fake
+def _(x, T_in, K, stride, dilation, padding, lens):
+    T_out = (T_in + 2 * padding - dilation * (K - 1) - 1) // stride + 1
+    return x.new_empty((x.shape[0], (x.shape[1] * K + 7) // 8 * 8, row_pitch(max(T_out, 1))))
 
 
 @torch.library.custom_op(f"{NS}::gather_rows", mutates_args=())

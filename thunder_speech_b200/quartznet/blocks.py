@@ -59,8 +59,17 @@ class MaskedConv1d(nn.Module):
                 w = conv.weight.detach()[:, :, 0].to(rows.dtype).contiguous()
                 bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
                 out = ops.pw_gemm(w, rows, None, None, T, bias, None, True, False, None, None, None)
+            elif conv.groups == 1:     # full convolution: im2col rows + one GEMM over Cin * K channels
+                cols = ops.im2col_rows(rows, T, self.kernel_size, self.stride, self.dilation, self.padding, None)
+                w = conv.weight.detach().float().reshape(conv.out_channels, -1)
+                if w.shape[1] != cols.shape[1]:
+                    w = torch.nn.functional.pad(w, (0, cols.shape[1] - w.shape[1]))
+                bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+                T_out = conv_out_length(T, self.kernel_size, self.stride, self.padding, self.dilation)
+                out = ops.pw_gemm(w.to(rows.dtype).contiguous(), cols, None, None, T_out, bias, None, True, False, None, None,
+                                  None)
             else:
-                raise NotImplementedError("stand-alone MaskedConv1d supports depthwise and 1x1 convolutions")
+                raise NotImplementedError("stand-alone MaskedConv1d supports depthwise, 1x1 and ungrouped convolutions")
         return out, self.get_seq_len(lengths)
 
 

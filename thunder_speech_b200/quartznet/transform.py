@@ -248,12 +248,19 @@ class _FusedFilterbank(nn.Sequential):
         ps: PowerSpectrum = self[1]
         norm: FeatureBatchNormalizer = self[3]
         with torch.no_grad():
-            if self.training and dither.dither != 0:
-                audio = dither(audio)
+            # train(): DitherAudio's noise is drawn INSIDE the feature kernel (counter-based normals keyed by torch's seed
+            # and a device-resident step counter that advances on the stream, so captured graphs draw fresh noise per replay)
+            dth = float(dither.dither) if self.training else 0.0
+            state = None
+            if dth != 0.0:
+                state = self.__dict__.get("_dither_state")
+                if state is None or state.device != audio.device:
+                    state = self.__dict__["_dither_state"] = torch.zeros((1,), dtype=torch.int64, device=audio.device)
+                state.add_(0x9E3779B97F4A7C15 - (1 << 64))      # odd increment (golden ratio), wraps mod 2^64
             t = self._device_tables(audio.device)
             from .. import get_stft_kernel
 
-            if get_stft_kernel() == "dft" and t["dft_ok"] and audio.shape[-1] > ps.n_fft // 2:
+            if dth == 0.0 and get_stft_kernel() == "dft" and t["dft_ok"] and audio.shape[-1] > ps.n_fft // 2:
                 # STFT as a DFT-matrix contraction on the tensor cores + normaliser fed by that kernel's partial sums
                 feats, feat_len = torch.ops.thunder_b200.filterbank_dft(
                     audio, lengths, t["wplus"], t["wminus"], t["basis"], t["mel_w2"], t["mel_adv"],
@@ -263,7 +270,7 @@ class _FusedFilterbank(nn.Sequential):
                 feats, feat_len = torch.ops.thunder_b200.filterbank(
                     audio, lengths, t["window_full"], t["twiddle"], t["mel_start"], t["mel_count"], t["mel_off"],
                     t["mel_w"], ps.hop_length, float(pre.preemph), t["win_lo"], t["win_hi"], float(norm.div_guard),
-                    int(bf16_pitch), bool(f16))
+                    int(bf16_pitch), bool(f16), dth, (int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF) if dth != 0.0 else 0, state)
             if self.training and len(self) > 4:   # SpecCutout / SpecAugment: in place on the fresh feature tensor
                 from .spec_augment import apply_rects
 
