@@ -73,8 +73,9 @@ int ts_row_pitch(int T);
  *   mel_start/mel_count/mel_off [nfilt] i32, mel_w [nnz] f32: row-compressed filter bank, filter m
  *              covers FFT bins [mel_start[m], mel_start[m]+mel_count[m]) with weights mel_w[mel_off[m]..]
  *   logmel     [B, nfilt, F] f32 out, F = 1 + N / hop
- * Only n_fft == 512 is implemented (TS_ERR_UNSUPPORTED otherwise); N must exceed n_fft/2 like
- * torch.stft's reflect padding.  */
+ * n_fft == 512 (the reference's models) runs the packed radix-8 FFT kernel; any other even n_fft <= 8192 (the reference
+ * takes whatever torch.stft takes, transform.py:258-271) runs a direct DFT over the window support -- correct, not tuned.
+ * N must exceed n_fft/2 like torch.stft's reflect padding.  */
 int ts_logmel(const float* audio, int B, int N, int n_fft, int hop, float preemph,
               const float* window_full, int win_lo, int win_hi, const float* twiddle,
               const int32_t* mel_start, const int32_t* mel_count, const int32_t* mel_off,

@@ -68,6 +68,20 @@ def test_features_other_hop_and_window():
         assert emax < TOL and el2 < TOL, (win, hop, emax, el2)
 
 
+@pytest.mark.parametrize("n_fft,win,hop", [(1024, 400, 160), (256, 200, 80), (400, 400, 100), (2048, 1200, 320)])
+def test_features_any_n_fft(n_fft, win, hop):
+    """The reference takes whatever torch.stft takes (transform.py:258-271): every n_fft other than 512 runs the direct-DFT
+    kernel -- same 1e-4 bar, ragged lengths, reflect padding at both ends, power-of-two or not."""
+    x = synth.audio(3, 9000 + n_fft, n_fft, "noise")
+    N = x.shape[1]
+    lens = np.array([N, N // 2 + 3, 1], np.int64)
+    f, fl = run_cuda(x, lens, 64, n_window_size=win, n_window_stride=hop, n_fft=n_fft)
+    rf, rl = R.filterbank_features(x, lens, n_window_size=win, n_window_stride=hop, n_fft=n_fft)
+    assert f.shape == rf.shape and np.array_equal(fl, rl) and np.isfinite(f).all()
+    emax, el2 = rel_err(f, rf)
+    assert emax < TOL and el2 < TOL, (n_fft, emax, el2)
+
+
 def test_features_errors():
     with pytest.raises(ValueError):
         FilterbankFeatures(n_window_size=0)

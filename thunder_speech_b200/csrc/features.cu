@@ -91,6 +91,79 @@ __device__ __forceinline__ float dither_normal(unsigned long long seed, int s, i
   return e == 0 ? z.x : e == 1 ? z.y : e == 2 ? z.z : z.w;
 }
 
+// ---- any other n_fft (the reference takes whatever torch.stft takes, transform.py:258-271) -----------------------------
+// Direct DFT over the window support, one CTA per (utterance, GF frames): the windowed, pre-emphasised, reflect-padded
+// samples of the frames and the twiddle table sit in shared memory, every thread owns bins k, k + 256, ... and walks the
+// window once for all GF frames (the twiddle index advances by k modulo n_fft, no multiplication).  O(n_fft * win) per frame
+// instead of O(n_fft log n_fft): a correct, self-contained fallback (n_fft = 1024, win 400: ~2 ms for 64 x 20 s), not a
+// tuned kernel -- n_fft = 512, the only size the reference's models use, has the FFT kernel above.
+template <int GF>
+__global__ void __launch_bounds__(256)
+logmel_generic_kernel(const float* __restrict__ audio, int N, int F, int n_fft, int hop, float preemph,
+                      const float* __restrict__ window_full, int win_lo, int win_hi, const float2* __restrict__ twiddle,
+                      const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
+                      const int32_t* __restrict__ mel_off, const float* __restrict__ mel_w, int nfilt,
+                      float* __restrict__ logmel, float dither, unsigned long long seed,
+                      const unsigned long long* __restrict__ seed_dev) {
+  extern __shared__ __align__(16) float smem[];
+  const int wlen = win_hi - win_lo, nbins = n_fft / 2 + 1;
+  float2* tw = reinterpret_cast<float2*>(smem);          // [n_fft]
+  float* v = smem + 2 * n_fft;                            // [GF][wlen]
+  float* pw = v + GF * wlen;                              // [GF][nbins]
+  const int b = blockIdx.y, f0 = blockIdx.x * GF, tid = threadIdx.x;
+  const float* x = audio + (size_t)b * N;
+  if (dither != 0.f && seed_dev != nullptr) seed ^= *seed_dev;
+  for (int i = tid; i < n_fft; i += 256) tw[i] = twiddle[i];
+  for (int i = tid; i < GF * wlen; i += 256) {
+    const int g = i / wlen, n = win_lo + (i - g * wlen);
+    const int f = f0 + g;
+    float val = 0.f;
+    if (f < F) {
+      const int s = f * hop - n_fft / 2 + n;
+      const int r = s < 0 ? -s : (s >= N ? 2 * (N - 1) - s : s);      // reflect (torch.stft center=True)
+      float xr = x[r], xp = r >= 1 ? x[r - 1] : 0.f;
+      if (dither != 0.f) {
+        xr = fmaf(dither, dither_normal(seed, r, b), xr);
+        if (r >= 1) xp = fmaf(dither, dither_normal(seed, r - 1, b), xp);
+      }
+      val = window_full[n] * (r >= 1 ? xr - preemph * xp : xr);       // y[0] = x[0]
+    }
+    v[i] = val;
+  }
+  __syncthreads();
+  for (int k = tid; k < nbins; k += 256) {
+    float re[GF], im[GF];
+#pragma unroll
+    for (int g = 0; g < GF; ++g) re[g] = im[g] = 0.f;
+    int idx = (int)(((long long)k * win_lo) % n_fft);
+    for (int j = 0; j < wlen; ++j) {
+      const float2 t = tw[idx];
+#pragma unroll
+      for (int g = 0; g < GF; ++g) {
+        const float a = v[g * wlen + j];
+        re[g] = fmaf(a, t.x, re[g]);
+        im[g] = fmaf(a, t.y, im[g]);
+      }
+      idx += k;
+      if (idx >= n_fft) idx -= n_fft;
+    }
+#pragma unroll
+    for (int g = 0; g < GF; ++g) {
+      const float m = sqrtf(re[g] * re[g] + im[g] * im[g]);             // sqrt then square, transform.py:205-207
+      pw[g * nbins + k] = m * m;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < GF * nfilt; i += 256) {
+    const int m = i / GF, g = i - m * GF;                                // consecutive threads: consecutive frames
+    if (f0 + g >= F) continue;
+    const int st = mel_start[m], cnt = mel_count[m], off = mel_off[m];
+    float a = 0.f;
+    for (int j = 0; j < cnt; ++j) a = fmaf(mel_w[off + j], pw[g * nbins + st + j], a);
+    logmel[((size_t)b * nfilt + m) * F + f0 + g] = logf(a + 5.9604644775390625e-08f);
+  }
+}
+
 // Persistent kernel: each CTA loops over (utterance, 32-frame tile) work items.  The raw audio span of the NEXT item is
 // fetched with cp.async into the other half of a double buffer while the current item is transformed.
 //
@@ -487,9 +560,29 @@ static int logmel_launch(const float* audio, int B, int N, int n_fft, int hop, f
              TS_ERR_INVALID, "ts_logmel: null pointer");
   TS_REQUIRE(B > 0 && hop > 0 && nfilt > 0 && nnz > 0, TS_ERR_INVALID, "ts_logmel: bad sizes B=%d hop=%d nfilt=%d", B,
              hop, nfilt);
-  TS_REQUIRE(n_fft == feat::NFFT, TS_ERR_UNSUPPORTED, "ts_logmel: only n_fft=512 is implemented (got %d)", n_fft);
+  TS_REQUIRE(n_fft >= 2 && n_fft <= 8192 && n_fft % 2 == 0, TS_ERR_UNSUPPORTED, "ts_logmel: n_fft=%d is out of range (even, 2..8192)",
+             n_fft);
   TS_REQUIRE(N > n_fft / 2, TS_ERR_INVALID,
              "ts_logmel: reflect padding needs N > n_fft/2 (N=%d), same as torch.stft(center=True)", N);
+  if (n_fft != feat::NFFT) {   // direct-DFT fallback for every other size
+    TS_REQUIRE(0 <= win_lo && win_lo < win_hi && win_hi <= n_fft, TS_ERR_INVALID, "ts_logmel: bad window support [%d,%d)",
+               win_lo, win_hi);
+    const int F = 1 + N / hop, wlen = win_hi - win_lo, nbins = n_fft / 2 + 1;
+    auto smem_for = [&](int gf) { return (size_t)(2 * n_fft + gf * (wlen + nbins)) * sizeof(float); };
+    int gf = 8;
+    while (gf > 1 && smem_for(gf) > 200 * 1024) gf >>= 1;
+    TS_REQUIRE(smem_for(gf) <= 200 * 1024, TS_ERR_UNSUPPORTED, "ts_logmel: n_fft=%d needs %zu bytes of shared memory", n_fft,
+               smem_for(gf));
+    TS_REQUIRE(B <= 65535, TS_ERR_UNSUPPORTED, "ts_logmel: batch %d too large for the generic n_fft path", B);
+    auto kern = gf == 8 ? feat::logmel_generic_kernel<8> : gf == 4 ? feat::logmel_generic_kernel<4>
+              : gf == 2 ? feat::logmel_generic_kernel<2> : feat::logmel_generic_kernel<1>;
+    TS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(gf)));
+    kern<<<dim3(ceil_div(F, gf), B), 256, smem_for(gf), (cudaStream_t)stream>>>(
+        audio, N, F, n_fft, hop, preemph, window_full, win_lo, win_hi, reinterpret_cast<const float2*>(twiddle), mel_start,
+        mel_count, mel_off, mel_w, nfilt, logmel, dither, seed, seed_dev);
+    TS_LAUNCH_CHECK("logmel_generic_kernel");
+    return TS_OK;
+  }
   TS_REQUIRE(nfilt <= feat::MAX_NFILT && nnz <= feat::MAX_NNZ, TS_ERR_UNSUPPORTED,
              "ts_logmel: filter bank too dense (nfilt=%d nnz=%d, limits %d/%d)", nfilt, nnz, feat::MAX_NFILT,
              feat::MAX_NNZ);
