@@ -330,6 +330,14 @@ def test_text_encode_known_answers_and_tokenizers(tmp_path):
         bpe = BatchTextTransformer(["▁the", "s", "t", "▁ca"], sentencepiece_model=sp)
         assert bpe.tokenizer("the cats") == ["▁the", "▁ca", "t", "s"]
         assert bpe.encode(["the cats"])[0].tolist() == [[0, 3, 2, 1]]
+        # from_sentencepiece (text_processing/transform.py:124-150): tokenizer.vocab lines "piece<TAB>score", specials skipped
+        import shutil
+
+        shutil.copy(sp, tmp_path / "tokenizer.model")
+        (tmp_path / "tokenizer.vocab").write_text("<unk>\t0\n<s>\t0\n</s>\t0\n▁the\t-1.5\ns\t-2\nt\t-2.5\n▁ca\t-3\n",
+                                                  encoding="utf-8")
+        fsp = BatchTextTransformer.from_sentencepiece(str(tmp_path))
+        assert list(fsp.vocab.itos[:4]) == ["▁the", "s", "t", "▁ca"] and fsp.encode(["the cats"])[0].tolist() == [[0, 3, 2, 1]]
 
 
 def test_product_code_never_touches_the_oracle_or_the_reference():

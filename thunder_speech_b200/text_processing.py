@@ -104,6 +104,16 @@ class BatchTextTransformer(nn.Module):
         else:
             self.tokenizer = char_tokenizer
 
+    @classmethod
+    def from_sentencepiece(cls, output_dir: str) -> "BatchTextTransformer":
+        """Vocabulary and tokenizer from a sentencepiece training output folder (``tokenizer.vocab`` + ``tokenizer.model``),
+        like the reference's classmethod (text_processing/transform.py:124-150): one piece per line (first tab-separated
+        field), sentencepiece's own ``<s>``, ``</s>``, ``<pad>``, ``<unk>`` entries skipped."""
+        skip = ("<s>", "</s>", "<pad>", "<unk>")
+        with open(f"{output_dir}/tokenizer.vocab", "r", encoding="utf-8") as f:
+            pieces = [line.split("\t")[0] for line in f]
+        return cls(tokens=[p for p in pieces if p not in skip], sentencepiece_model=f"{output_dir}/tokenizer.model")
+
     def encode(self, items: List[str], return_length: bool = True, device=None) -> Union[Tensor, Tuple[Tensor, Tensor]]:
         """List of texts -> padded int64 ``[B, Lmax]`` (pad value ``pad_idx``) and lengths (transform.py:65-91)."""
         import torch
