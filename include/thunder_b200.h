@@ -159,6 +159,10 @@ int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, const float*
  * depend on the order in which the tiles of an utterance finish; `se_scale` [B, Cout] + `y1` bf16 rows:
  * out = epi(acc + shift + se_scale * y1). */
 #define TS_PW_RELU 1
+/* the caller guarantees that w0 / w1 were written BEFORE anything still in flight on this stream (folded inference weights,
+ * completed by a stream synchronisation when the plan was built): the weight-stationary kernel may then copy them into
+ * tensor memory before griddepcontrol.wait, i.e. while the previous kernel is still running */
+#define TS_PW_CONST_WEIGHTS 4
 /* flags: TS_PW_RELU = ReLU in the epilogue; TS_ROWS_F16 = w*, x*, y1 (and a 16-bit `out`, out_dtype = TS_F16) are IEEE
  * fp16 instead of bf16 (same kernels: the tcgen05 kind::f16 instruction descriptor selects the operand format). */
 int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,

@@ -220,6 +220,45 @@ def test_pw_gemm_squeeze_excite_epilogues():
     assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
 
 
+def test_pw_gemm_weights_in_tensor_memory_variant_is_bit_identical():
+    """Option pw_ws: the weight-stationary pair GEMM (csrc/pwgemm4.cu: weights copied once into tensor memory, tcgen05.mma
+    with A from TMEM, 256 x 128 tiles) for K <= 512 -- same k order, same epilogue, so the same bits as the streaming pair
+    kernel (the SE pool agrees to fp32 rounding): plain / residual segment + ReLU + tail mask / SE pool / SE gate, ragged channel counts, both row formats, and the
+    const-weights (copy before griddepcontrol.wait) and produced-weights orders."""
+    from thunder_speech_b200 import _lib
+
+    rng = np.random.default_rng(44)
+    B, T = 5, 700
+    lens = dev(np.array([700, 512, 129, 64, 0], np.int64), torch.int32)
+    cases = [(256, 256, 0), (512, 384, 128), (264, 72, 0), (1024, 512, 0), (384, 256, 256)]
+    try:
+        for dt in (torch.bfloat16, torch.float16):
+            for Cout, c0, c1 in cases:
+                w0 = dev((rng.standard_normal((Cout, c0)) / np.sqrt(c0)).astype(np.float32), dt)
+                x0 = to_rows(rng.standard_normal((B, c0, T)).astype(np.float32)).to(dt)
+                w1 = dev((rng.standard_normal((Cout, c1)) / np.sqrt(c1)).astype(np.float32), dt) if c1 else None
+                x1 = to_rows(rng.standard_normal((B, c1, T)).astype(np.float32)).to(dt) if c1 else None
+                shift = dev(rng.standard_normal(Cout).astype(np.float32))
+                gate = dev(rng.uniform(0.1, 0.9, (B, Cout)).astype(np.float32))
+                outs = {}
+                for ws in (0, 1):
+                    _lib.set_option("pw_ws", ws)
+                    pool = torch.zeros((B, Cout), device="cuda", dtype=torch.int64)
+                    y = ops.pw_gemm(w0, x0, w1, x1, T, shift, lens, False, True, None, None, None, ws == 1)
+                    y1 = ops.pw_gemm(w0, x0, None, None, T, shift, None, False, False, pool, None, None)
+                    z = ops.pw_gemm(w0, x0, None, None, T, shift, lens, False, True, None, gate, y1, True)
+                    outs[ws] = (y, y1, pool, z)
+                torch.cuda.synchronize()
+                for i, (a, b) in enumerate(zip(outs[0], outs[1])):
+                    if i == 2:   # SE pool: per-thread fp32 partial sums cover 128 vs 64 frames before the fixed-point add
+                        fa, fb = ops.se_pool_to_float(a), ops.se_pool_to_float(b)
+                        assert (fa - fb).abs().max() <= 1e-5 * fa.abs().max(), (dt, Cout, c0, c1)
+                    else:
+                        assert torch.equal(a, b), (dt, Cout, c0, c1, i)
+    finally:
+        _lib.set_option("pw_ws", 0)
+
+
 def test_se_fc_matches_oracle():
     rng = np.random.default_rng(7)
     B, C, H, T = 3, 64, 8, 41

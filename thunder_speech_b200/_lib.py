@@ -27,6 +27,7 @@ TS_F16 = 4
 TS_DW_INPUT_PREMASKED = 1
 TS_ROWS_F16 = 2
 TS_PW_RELU = 1
+TS_PW_CONST_WEIGHTS = 4
 
 _lib = None
 

@@ -33,6 +33,7 @@ static Option g_options[] = {
     {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
     {"dwp_nbuf", {0}},        // persistent Toeplitz kernel: Toeplitz buffers (0 = auto: 2 when NQ <= 3), experiment
     {"dwp_nstage", {0}},      // ... input stages (0 = auto)
+    {"pw_ws", {0}},           // pair GEMM with the weights in tensor memory (pwgemm4.cu) for K <= 512
     {"small", {0}},           // small-footprint co-resident kernels: 0 never, 1 when B x pitch <= small_frames, 2 always
     {"small_frames", {32768}},
     {"serpentine", {1}},      // alternate the utterance walk direction between consecutive launches (L2 reuse)
@@ -60,6 +61,7 @@ int small_footprint(long long frames) {
 }
 int option_dwp_nbuf() { return opt("dwp_nbuf").load(std::memory_order_relaxed); }
 int option_dwp_nstage() { return opt("dwp_nstage").load(std::memory_order_relaxed); }
+int option_pw_ws() { return opt("pw_ws").load(std::memory_order_relaxed); }
 int option_serpentine() { return opt("serpentine").load(std::memory_order_relaxed); }
 int option_dbg() { return opt("dbg").load(std::memory_order_relaxed); }
 static std::atomic<unsigned> g_walk{0};

@@ -227,7 +227,7 @@ int launch_pw_gemm_big(const void* w0, const void* x0, int cin0, int x0_pitch, c
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st, float* stats = nullptr, int f16 = 0);
+                        cudaStream_t st, float* stats = nullptr, int f16 = 0, int wconst = 0);
 int option_pw_pair();
 }
 using namespace ts;
@@ -274,7 +274,8 @@ extern "C" int ts_pw_gemm(const void* w0, const void* x0, int cin0, int x0_pitch
   if (out16 && option_pw_big() && option_pw_pair() > 0 &&
       (option_pw_pair() >= 2 || cin0 + cin1 >= 1024 || f16)) {
     const int rc = launch_pw_gemm_pair(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out,
-                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream, nullptr, f16);
+                                       out_pitch, relu, pool, se_scale, y1, y1_pitch, (cudaStream_t)stream, nullptr, f16,
+                                       (flags & TS_PW_CONST_WEIGHTS) ? 1 : 0);
     if (rc != TS_ERR_UNSUPPORTED) return rc;
   }
   if (out16 && !f16 && option_pw_big()) {

@@ -445,14 +445,25 @@ pw_gemm_pair_kernel(const __grid_constant__ Params p) {
 }  // namespace pw3
 
 int option_pw_resident();
+int option_pw_ws();
+int launch_pw_gemm_ws(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
+                      int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
+                      int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
+                      cudaStream_t st, int f16, int wconst);
 int small_footprint(long long frames);
 
 // bf16-row outputs with Cout > 128 on CTA pairs; TS_ERR_UNSUPPORTED otherwise (caller falls back)
 int launch_pw_gemm_pair(const void* w0, const void* x0, int cin0, int x0_pitch, const void* w1, const void* x1, int cin1,
                         int x1_pitch, int B, int Cout, int T, const float* shift, const int32_t* lens, void* out,
                         int out_pitch, int relu, unsigned long long* pool, const float* se_scale, const void* y1, int y1_pitch,
-                        cudaStream_t st, float* stats, int f16) {
+                        cudaStream_t st, float* stats, int f16, int wconst) {
   if (Cout <= 128 || out_pitch % 64 != 0) return TS_ERR_UNSUPPORTED;
+  // K <= 512: the weight-stationary kernel with the weights in tensor memory (pwgemm4.cu)
+  if (stats == nullptr && option_pw_ws() != 0 && small_footprint((long long)B * out_pitch) == 0) {
+    const int rc = launch_pw_gemm_ws(w0, x0, cin0, x0_pitch, w1, x1, cin1, x1_pitch, B, Cout, T, shift, lens, out, out_pitch,
+                                     relu, pool, se_scale, y1, y1_pitch, st, f16, wconst);
+    if (rc != TS_ERR_UNSUPPORTED) return rc;
+  }
   pw3::Params p;
   memset(&p, 0, sizeof(p));
   int rc;

@@ -169,7 +169,7 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
         else:
             a, Ta, la = cur, Tc, lc
         if not last:
-            cur = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, la, False, True, None, None, None)
+            cur = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, la, False, True, None, None, None, True)
             Tc, lc = Ta, la
             continue
         out_lens = la if zero_tail else None
@@ -181,17 +181,17 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
         if plan.se_w1 is None:
             if xr is not None:
                 out = ops.pw_gemm(sb.pw_w, a, plan.res_w, xr, Ta, plan.total_shift, out_lens, False, True, None, None,
-                                  None)
+                                  None, True)
             else:
-                out = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, out_lens, False, True, None, None, None)
+                out = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, out_lens, False, True, None, None, None, True)
         else:
             B = a.shape[0]
             pool = torch.zeros((B, plan.out_channels), device=a.device, dtype=torch.int64)   # fixed-point sums
-            y1 = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, None, False, False, pool, None, None)
+            y1 = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, None, False, False, pool, None, None, True)
             gate = ops.se_fc(pool, Ta, plan.se_w1, plan.se_w2)
             if xr is not None:
                 out = ops.pw_gemm(plan.res_w, xr, None, None, Ta, plan.res_shift, out_lens, False, True, None, gate,
-                                  y1)
+                                  y1, True)
             else:
                 out = ops.se_apply(y1, gate, out_lens, True)
         Tc, lc = Ta, la
@@ -212,6 +212,9 @@ class PlannedBlock(nn.Module):
         if cached is None or cached[0] != key:
             cached = (key, build_block_plan(self, dtype))
             object.__setattr__(self, "_plan_cache", cached)
+            # the folded operands are complete before any kernel that is told they are constants (TS_PW_CONST_WEIGHTS) starts
+            if cached[1].subs[0].pw_w.is_cuda and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(cached[1].subs[0].pw_w.device).synchronize()
         return cached[1]
 
     def _check_eval(self):

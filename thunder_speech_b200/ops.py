@@ -254,8 +254,10 @@ def _(x, T_in, weight, stride, dilation, padding, lens, premasked=False):
 @torch.library.custom_op(f"{NS}::pw_gemm", mutates_args=("pool",))
 def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], T: int, shift: Optional[Tensor],
             lens: Optional[Tensor], out_f32: bool, relu: bool, pool: Optional[Tensor], se_scale: Optional[Tensor],
-            y1: Optional[Tensor]) -> Tensor:
+            y1: Optional[Tensor], const_weights: bool = False) -> Tensor:
     """tcgen05 pointwise GEMM with fused BN-shift / residual segment / ReLU / tail mask / SE epilogues.
+    ``const_weights``: ``w0`` / ``w1`` were complete before anything still in flight on the stream (folded inference plans,
+    built and synchronised once) -- lets the weight-stationary kernel fetch them under the previous kernel's tail.
     ``w*`` bf16 ``[Cout, Cin]`` (BN scale folded in), ``x*`` bf16 rows ``[B, Cin, pitch]``.  ``pool`` (SqueezeExcite
     squeeze) is a zeroed int64 ``[B, Cout]``: fixed-point sums in units of 2^-32 (``se_pool_to_float``), accumulated with
     integer atomics so that the result does not depend on tile order."""
@@ -284,13 +286,14 @@ def pw_gemm(w0: Tensor, x0: Tensor, w1: Optional[Tensor], x1: Optional[Tensor], 
     with _timed("pw_gemm", bytes=nbytes, flops=2 * B * T * kin * Cout, K=kin, C=Cout, T=T):
         _lib.check(_lib.lib().ts_pw_gemm(_ptr(w0), _ptr(x0), cin0, p0, P(w1), P(x1), cin1, p1, B, Cout, T, P(shift),
                                          P(lens), _ptr(out), dt, pitch,
-                                         (_lib.TS_PW_RELU if relu else 0) | _f16_flag(x0), P(pool), P(se_scale), P(y1),
+                                         (_lib.TS_PW_RELU if relu else 0) | _f16_flag(x0)
+                                         | (_lib.TS_PW_CONST_WEIGHTS if const_weights else 0), P(pool), P(se_scale), P(y1),
                                          y1.shape[2] if y1 is not None else 0, _stream()), "ts_pw_gemm")
     return out
 
 
 @pw_gemm.register_fake
-def _(w0, x0, w1, x1, T, shift, lens, out_f32, relu, pool, se_scale, y1):
+def _(w0, x0, w1, x1, T, shift, lens, out_f32, relu, pool, se_scale, y1, const_weights=False):
     B, Cout = x0.shape[0], w0.shape[0]
     if out_f32:
         return x0.new_empty((B, Cout, T), dtype=torch.float32)
