@@ -147,8 +147,8 @@ def _next_lens(lens: Optional[Tensor], K: int, S: int, D: int, P: int) -> Option
     return ops.conv_lengths(lens, K, S, D, P)
 
 
-def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool
-              ) -> Tuple[Tensor, int, Optional[Tensor]]:
+def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool,
+              pool: Optional[Tensor] = None) -> Tuple[Tensor, int, Optional[Tensor]]:
     """``x``: bf16 rows ``[B, Cin, pitch]`` holding ``T`` frames, already zero beyond ``lens`` (i32 ``[B]``;
     ``None`` = every frame valid).  Returns ``(y rows, T_out, lens_out)``.  ``zero_tail``: store the block output
     with frames beyond ``lens_out`` zeroed (legal whenever the consumer is another MaskedConv1d)."""
@@ -186,7 +186,8 @@ def run_block(plan: BlockPlan, x: Tensor, T: int, lens: Optional[Tensor], zero_t
                 out = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, out_lens, False, True, None, None, None, True)
         else:
             B = a.shape[0]
-            pool = torch.zeros((B, plan.out_channels), device=a.device, dtype=torch.int64)   # fixed-point sums
+            if pool is None:    # (an encoder hands every SE block a slice of ONE buffer it zeroed with a single fill)
+                pool = torch.zeros((B, plan.out_channels), device=a.device, dtype=torch.int64)   # fixed-point sums
             y1 = ops.pw_gemm(sb.pw_w, a, None, None, Ta, sb.shift, None, False, False, pool, None, None, True)
             gate = ops.se_fc(pool, Ta, plan.se_w1, plan.se_w2)
             if xr is not None:
@@ -224,10 +225,16 @@ class PlannedBlock(nn.Module):
                 "batch-statistics BatchNorm and the backward kernels run through CTCModule.training_step / "
                 "thunder_speech_b200.train.CTCTrainStep (whole model) or train.BlockTrainer (one block).")
 
-    def forward_rows(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool):
+    def forward_rows(self, x: Tensor, T: int, lens: Optional[Tensor], zero_tail: bool, pool: Optional[Tensor] = None):
+        """``pool``: a zeroed int64 ``[B, out_channels]`` SqueezeExcite accumulator owned by the caller (optional)."""
         self._check_eval()
         with torch.no_grad():
-            return run_block(self._plan(x.dtype), x, T, lens, zero_tail)
+            return run_block(self._plan(x.dtype), x, T, lens, zero_tail, pool)
+
+    def se_channels(self, dtype: Optional[torch.dtype] = None) -> int:
+        """Channels of this block's SqueezeExcite pool (0 without SE): lets an encoder zero all pools with one fill."""
+        plan = self._plan(dtype)
+        return plan.out_channels if plan.se_w1 is not None else 0
 
     def out_lengths(self, lengths: Tensor) -> Tensor:
         """Lengths after the main branch, computed with the reference's own formula on the caller's tensor

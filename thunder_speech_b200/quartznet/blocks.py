@@ -157,8 +157,17 @@ class EncoderBase(MultiSequential):
         zeroed (every consumer is a MaskedConv1d); the final block's output is left unmasked, like the
         reference, because the decoder is a plain Conv1d."""
         blocks = list(self.children())
+        # SqueezeExcite pools of all blocks: ONE zero-fill per forward instead of one per block (23 on Citrinet-1024)
+        B = rows.shape[0]
+        se_c = [blk.se_channels(rows.dtype) for blk in blocks]
+        pools = torch.zeros((B * sum(se_c),), device=rows.device, dtype=torch.int64) if any(se_c) else None
+        off = 0
         for i, blk in enumerate(blocks):
-            rows, T, lens = blk.forward_rows(rows, T, lens, zero_tail=(i != len(blocks) - 1))
+            pool = None
+            if se_c[i]:
+                pool = pools[off:off + B * se_c[i]].view(B, se_c[i])
+                off += B * se_c[i]
+            rows, T, lens = blk.forward_rows(rows, T, lens, zero_tail=(i != len(blocks) - 1), pool=pool)
         return rows, T, lens
 
     def out_lengths(self, lengths: Tensor) -> Tensor:
