@@ -31,6 +31,8 @@ static Option g_options[] = {
     {"dw_base_offset", {0}},
     {"dw_share_halo", {1}},
     {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
+    {"dw_nstage", {0}},       // per-channel Toeplitz kernel: input stages (0 = default 3)
+    {"tma_l2", {3}},          // L2 promotion of every tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
     {"dwp_nbuf", {0}},        // persistent Toeplitz kernel: Toeplitz buffers (0 = auto: 2 when NQ <= 3), experiment
     {"dwp_nstage", {0}},      // ... input stages (0 = auto)
     {"pw_ws", {0}},           // pair GEMM with the weights in tensor memory (pwgemm4.cu) for K <= 512
@@ -59,6 +61,8 @@ int small_footprint(long long frames) {
   const int m = opt("small").load(std::memory_order_relaxed);
   return m >= 2 || (m == 1 && frames <= (long long)opt("small_frames").load(std::memory_order_relaxed));
 }
+int option_dw_nstage() { return opt("dw_nstage").load(std::memory_order_relaxed); }
+int option_tma_l2() { return opt("tma_l2").load(std::memory_order_relaxed); }
 int option_dwp_nbuf() { return opt("dwp_nbuf").load(std::memory_order_relaxed); }
 int option_dwp_nstage() { return opt("dwp_nstage").load(std::memory_order_relaxed); }
 int option_pw_ws() { return opt("pw_ws").load(std::memory_order_relaxed); }

@@ -19,14 +19,15 @@ namespace dwt2 {
 constexpr int L = 64;
 constexpr int MROWS = 128;
 constexpr int A_STAGE = 17 * 1024;     // 130 rows x 128 B rounded up to a multiple of 1024
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 3;              // default input stages (option dw_nstage: 2..4, clamped to what two CTAs per SM allow)
+constexpr int MAX_NSTAGE = 4;
 constexpr int BQ = 64 * 128;           // one Toeplitz block: 64 rows (r) x 64 k (j) bf16 = 8 KB
 constexpr int MAX_NQ = 5;              // Toeplitz blocks: left halo + centre + right halo windows (3 for K <= 129, dilation 1)
 constexpr int OUT_STAGE = MROWS * 128; // 16 KB
 constexpr int ACC_STAGES = 4;
 constexpr int TMEM_COLS = ACC_STAGES * L;  // 256
 constexpr int THREADS = 256;
-__host__ __device__ constexpr int smem_bytes(int nq) { return NSTAGE * A_STAGE + nq * BQ + OUT_STAGE + 256 + 1024; }
+__host__ __device__ constexpr int smem_bytes(int nq, int nstage) { return nstage * A_STAGE + nq * BQ + OUT_STAGE + 256 + 1024; }
 
 struct Params {
   CUtensorMap in, out;   // (64 frames, W windows, C, B), box (64, R, 1, NB)
@@ -35,6 +36,7 @@ struct Params {
   int B, C, T, K, P, D;
   int W, R, NB;
   int HL, NQ;            // left halo windows = ceil(P / 64); Toeplitz blocks = HL + 1 + (63 + P) / 64
+  int nstage;            // input stages of this launch
   int tiles_per_chan, tiles_per_cta;
   int f16;               // rows (and the Toeplitz blocks) are IEEE fp16 instead of bf16
   int rev;               // walk the utterance tiles from the far end (see next_walk_reversed())
@@ -84,11 +86,12 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
+  const int NSTAGE = p.nstage;           // shadows the namespace default: stage count of THIS launch
   uint8_t* sB = sA + NSTAGE * A_STAGE;
   uint8_t* sO = sB + p.NQ * BQ;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sO + OUT_STAGE);
-  uint64_t* empty_bar = full_bar + NSTAGE;
-  uint64_t* acc_full = empty_bar + NSTAGE;
+  uint64_t* empty_bar = full_bar + MAX_NSTAGE;
+  uint64_t* acc_full = empty_bar + MAX_NSTAGE;
   uint64_t* acc_empty = acc_full + ACC_STAGES;
   uint64_t* b_ready = acc_empty + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 1);
@@ -305,6 +308,7 @@ dw_tma_kernel(const __grid_constant__ Params p) {
 int option_dw_base_offset();
 int option_dw_share_halo();
 int option_dw_pro();
+int option_dw_nstage();
 
 int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                   const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16) {
@@ -358,17 +362,20 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
   static bool attr_set = false;
   if (!attr_set) {
     TS_CUDA(cudaFuncSetAttribute(dwt2::dw_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dwt2::smem_bytes(3)));
+                                 dwt2::smem_bytes(3, dwt2::MAX_NSTAGE)));
     TS_CUDA(cudaFuncSetAttribute(dwt2::dw_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dwt2::smem_bytes(dwt2::MAX_NQ)));
+                                 dwt2::smem_bytes(dwt2::MAX_NQ, dwt2::MAX_NSTAGE)));
     attr_set = true;
   }
   dim3 grid(C, groups);
+  p.nstage = option_dw_nstage() > 0 ? option_dw_nstage() : dwt2::NSTAGE;
+  if (p.nstage > dwt2::MAX_NSTAGE) p.nstage = dwt2::MAX_NSTAGE;
+  while (p.nstage > 2 && 2 * (dwt2::smem_bytes(p.NQ, p.nstage) + 1024) > 232448) --p.nstage;   // two CTAs per SM
   p.trace = trace_next_slot(3, (unsigned)(C * groups));
   if (p.NQ <= 3)
-    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<3>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ), st, option_pdl() != 0, p));
+    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<3>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ, p.nstage), st, option_pdl() != 0, p));
   else
-    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<5>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ), st, option_pdl() != 0, p));
+    TS_CUDA(launch_pdl(dwt2::dw_tma_kernel<5>, grid, dim3(dwt2::THREADS), dwt2::smem_bytes(p.NQ, p.nstage), st, option_pdl() != 0, p));
   TS_LAUNCH_CHECK("dw_tma_kernel");
   return TS_OK;
 }

@@ -9,6 +9,7 @@
 #include "ts_common.cuh"
 
 namespace ts {
+int option_tma_l2();
 namespace tma {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -35,7 +36,7 @@ inline int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  (CUtensorMapL2promotion)option_tma_l2(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TS_REQUIRE(r == CUDA_SUCCESS, TS_ERR_INVALID,
              "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu strides %llu %llu box %u %u %u", (int)r,
              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull,
