@@ -251,6 +251,21 @@ assert fm.seen == [hi - lo, hi - lo, shard_bounds(5, 2, dist.get_rank())[1] - sh
 fm2 = FakeModule()
 mine = [b[slice(*shard_bounds(b.shape[0], 2, dist.get_rank()))] for b in batches]
 assert sharded_predict_stream(fm2, iter(mine), presharded=True) == got
+# the overlapped gather falls back to ONE all_gather_object when a later batch outgrows the slot agreed on the first batch,
+# or a transcript contains the separator: same result, nothing truncated; empty transcripts and empty shards survive
+class TextModule:
+    def __init__(self, rows): self.rows = rows
+    def predict_stream(self, batches, depth=3):
+        for xb, r in zip(batches, self.rows):
+            yield list(r)
+r = dist.get_rank()
+rows = [["a%d" % r, ""], ["b" * (5000 + r), "c"], ["d", "e%d" % r]]
+exp = [["a0", "", "a1", ""], ["b" * 5000, "c", "b" * 5001, "c"], ["d", "e0", "d", "e1"]]
+assert sharded_predict_stream(TextModule(rows), iter([audio] * 3), presharded=True) == exp
+rows = [["x", "y\x00z"] if r == 1 else ["x", "y"], [] if r == 0 else ["only%d" % r]]
+assert sharded_predict_stream(TextModule(rows), iter([audio] * 2), presharded=True) == [["x", "y", "x", "y\x00z"], ["only1"]]
+rows = [["é字 %d" % r, ""], [], ["", ""]]
+assert sharded_predict_stream(TextModule(rows), iter([audio] * 3), presharded=True) == [["é字 0", "", "é字 1", ""], [], ["", "", "", ""]]
 dist.barrier(); dist.destroy_process_group()
 print("rank", sys.argv[3], "ok")
 """

@@ -37,13 +37,134 @@ def sharded_predict(predict: Callable[[torch.Tensor], List[str]], audio: torch.T
     return out
 
 
+class _TranscriptGatherer:
+    """Gathers the transcripts of a stream of batches WHILE the stream runs: after a batch is detokenised its strings are
+    packed into one byte blob (NUL separated, 16-byte header = blob length, number of strings) and exchanged with ONE
+    fixed-size tensor all-gather -- on a side CUDA stream with pinned staging under NCCL (asynchronous for the host and for
+    the compute stream), synchronously on CPU tensors under gloo.  At the end of the stream only the last batch's exchange
+    is still in flight; one ``all_gather_object`` of the whole stream (what round 1 did) costs 4-9 ms there, 10-18 % of a
+    20-step run at 32 utterances per GPU.  The slot capacity is agreed once, from the first batch ever pushed (1.5 x the
+    largest blob + slack), and again after a stream that overflowed; a blob that does not fit, or a transcript containing NUL, flags the stream and every rank falls
+    back to the single ``all_gather_object`` -- same result, never a truncated transcript."""
+
+    SLOTS = 4
+
+    def __init__(self, group, world: int, rank: int):
+        self.group, self.world, self.rank = group, world, rank
+        self.cuda = dist.get_backend(group) == "nccl"
+        self.cap = 0
+        self.slots: list = []
+        self.stream = torch.cuda.Stream() if self.cuda else None
+
+    def _alloc(self, cap: int) -> None:
+        self.cap = cap
+        n = cap + 16
+        self.slots = []
+        for _ in range(self.SLOTS):
+            if self.cuda:
+                hin = torch.empty(n, dtype=torch.uint8).pin_memory()
+                hout = torch.empty(self.world * n, dtype=torch.uint8).pin_memory()
+                din = torch.empty(n, dtype=torch.uint8, device="cuda")
+                dout = torch.empty(self.world * n, dtype=torch.uint8, device="cuda")
+                self.slots.append(dict(hin=hin, hout=hout, din=din, dout=dout, ev=torch.cuda.Event(), busy=False))
+            else:
+                self.slots.append(dict(hin=torch.empty(n, dtype=torch.uint8), hout=torch.empty(self.world * n, dtype=torch.uint8),
+                                       busy=False))
+
+    def begin(self) -> None:
+        self.results: list = []      # per pushed batch: bytes of the gathered buffer (filled when its slot is recycled / at the end)
+        self.pending: list = []      # (batch index, slot)
+        self.failed = False
+        self.count = 0
+
+    def _agree_capacity(self, need: int) -> None:
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(need), group=self.group)
+        cap = (int(1.5 * max(sizes)) + 256 + 1023) // 1024 * 1024
+        if cap > self.cap:
+            self._alloc(cap)
+
+    def _retire(self, idx: int, slot: dict) -> None:
+        if self.cuda:
+            slot["ev"].synchronize()
+        self.results[idx] = bytes(slot["hout"].numpy().tobytes())
+        slot["busy"] = False
+
+    def push(self, texts: Sequence[str]) -> None:
+        import numpy as np
+
+        ok = all("\x00" not in t for t in texts)
+        blob = b"\x00".join(t.encode("utf-8") for t in texts) if ok else b""
+        if self.count == 0 and self.cap == 0:    # once per gatherer (and again after a stream that overflowed, see finish())
+            self._agree_capacity(len(blob))
+        idx = self.count
+        self.count += 1
+        self.results.append(None)
+        if not ok or len(blob) > self.cap:
+            self.failed = True       # still take part in the exchange (header says "overflow") so that every rank learns it
+            blob, n_texts = b"", -1
+        else:
+            n_texts = len(texts)
+        slot = self.slots[idx % self.SLOTS]
+        if slot["busy"]:
+            old = [pi for pi in self.pending if pi[1] is slot][0]
+            self.pending.remove(old)
+            self._retire(old[0], slot)
+        hin = slot["hin"].numpy()
+        hin[:16] = np.array([len(blob), n_texts], dtype=np.int64).view(np.uint8)
+        hin[16:16 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        n = self.cap + 16
+        if self.cuda:
+            # (the blob is host data, complete before it is queued: no dependency on the compute stream in either direction)
+            with torch.cuda.stream(self.stream):
+                slot["din"].copy_(slot["hin"], non_blocking=True)
+                dist.all_gather_into_tensor(slot["dout"], slot["din"], group=self.group)
+                slot["hout"].copy_(slot["dout"], non_blocking=True)
+                slot["ev"].record(self.stream)
+        else:
+            parts = list(slot["hout"].view(self.world, n).unbind(0))
+            dist.all_gather(parts, slot["hin"], group=self.group)
+        slot["busy"] = True
+        self.pending.append((idx, slot))
+
+    def finish(self, mine: List[List[str]]) -> List[List[List[str]]]:
+        """-> per batch, per rank, the list of transcripts (falls back to one all_gather_object when any rank overflowed)."""
+        import numpy as np
+
+        for idx, slot in self.pending:
+            self._retire(idx, slot)
+        self.pending = []
+        n = self.cap + 16
+        out: List[List[List[str]]] = []
+        failed = self.failed
+        for buf in self.results:
+            a = np.frombuffer(buf, dtype=np.uint8).reshape(self.world, n)
+            row = []
+            for r in range(self.world):
+                ln, cnt = (int(v) for v in a[r, :16].view(np.int64))
+                if cnt < 0:
+                    failed = True
+                    break
+                row.append(a[r, 16:16 + ln].tobytes().decode("utf-8").split("\x00") if cnt > 0 else [])
+            out.append(row)
+        if failed:          # every rank saw the same headers, so every rank takes this branch
+            self.cap = 0    # ... and re-negotiates the slot size at the start of its next stream
+            parts: List[Sequence[Sequence[str]]] = [None] * self.world  # type: ignore[list-item]
+            dist.all_gather_object(parts, mine, group=self.group)
+            return [[list(parts[r][i]) for r in range(self.world)] for i in range(len(mine))]
+        return out
+
+
+_gatherers: dict = {}
+
+
 def sharded_predict_stream(module, batches, group=None, depth: int = 3, presharded: bool = False) -> List[List[str]]:
     """Strong-scaling serving loop (BASELINE configs 3 / 4: "batch-sharded at 1/2/4/8"): every rank runs
     ``module.predict_stream`` over ITS contiguous slice of each host batch ``[B, N]`` (``presharded=True``: the iterable
     already yields this rank's slice) -- H2D, graph replay, D2H and detokenisation of its own utterances, no data-path
-    collective -- and the transcripts of all batches are gathered ONCE at the end of the stream (one
-    ``all_gather_object``: the only exchange of the inference path).  Returns, on every rank, one list of ``B``
-    transcripts per batch in the original utterance order."""
+    collective -- and the transcripts are gathered on every rank: each batch's strings leave in one small tensor all-gather
+    as soon as they exist (`_TranscriptGatherer`: the only exchange of the inference path, overlapped with the stream).
+    Returns, on every rank, one list of ``B`` transcripts per batch in the original utterance order."""
     on = dist.is_available() and dist.is_initialized()
     world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
 
@@ -55,18 +176,20 @@ def sharded_predict_stream(module, batches, group=None, depth: int = 3, preshard
                 lo, hi = shard_bounds(xb.shape[0], world, rank)
                 yield xb[lo:hi]
 
-    mine = [texts for texts in module.predict_stream(local(batches), depth=depth)]
     if world == 1:
-        return mine
-    parts: List[Sequence[Sequence[str]]] = [None] * world  # type: ignore[list-item]
-    dist.all_gather_object(parts, mine, group=group)
-    out: List[List[str]] = []
-    for i in range(len(mine)):
-        row: List[str] = []
-        for p in parts:
-            row.extend(p[i])
-        out.append(row)
-    return out
+        return [texts for texts in module.predict_stream(local(batches), depth=depth)]
+    key = (id(group), world, rank)
+    g = _gatherers.get(key)
+    if g is None:
+        g = _gatherers[key] = _TranscriptGatherer(group, world, rank)
+    g.begin()
+    mine: List[List[str]] = []
+    for texts in module.predict_stream(local(batches), depth=depth):
+        mine.append(texts)
+        g.push(texts)
+    if not mine:
+        return []
+    return [[t for part in row for t in part] for row in g.finish(mine)]
 
 
 def flat_grad_views(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
