@@ -1,8 +1,8 @@
 """Batch sharding for multi-GPU inference: one process per GPU, every utterance is independent
 in eval mode (per-channel BatchNorm affine, per-utterance SqueezeExcite and feature normalisation), so the
-path shards with NO data-path collective.  The only exchange is gathering the transcripts (host strings) --
-``torch.distributed.all_gather_object`` over whatever backend the job runs (NCCL on the GPU box, gloo in the CPU
-tests)."""
+path shards with NO data-path collective.  The only exchange is gathering the transcripts (host strings): one
+``all_gather_object`` for a single batch, one small tensor all-gather per batch overlapped with the stream for the serving
+loop -- over whatever backend the job runs (NCCL on the GPU box, gloo in the CPU tests)."""
 from __future__ import annotations
 
 from typing import Callable, List, Sequence, Tuple
