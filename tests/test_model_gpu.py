@@ -158,6 +158,34 @@ def test_predict_matches_oracle_decode(golden_e2e, model):
     assert len([k for k in m._graphs if k[2] is not None]) == m.MAX_IN_PLACE_GRAPHS
 
 
+@pytest.mark.parametrize("model", ["qn5x5", "cn"])
+def test_experiment_knobs_do_not_change_results(model):
+    """The off-by-default design alternatives measured in DESIGN.md section 9 stay CORRECT: utterance chains on parallel graph
+    branches (CTCModule.graph_chains), the half-SM co-resident kernel variants (option small), the weights-in-tensor-memory
+    GEMM (option pw_ws) and the persistent Toeplitz kernel everywhere (dw_persist=2) give the ids of the default path."""
+    from thunder_speech_b200 import _lib
+
+    m, _ = build_qn5x5() if model == "qn5x5" else build_cn_small()
+    x = torch.from_numpy(synth.audio(6, 20000, 31, "tones")).cuda()
+    want = [t.clone() for t in m.predict_ids(x)]
+    try:
+        for chains in (2, 3, 6):
+            m.graph_chains = chains
+            got = m.predict_ids_graphed(x)
+            assert all(torch.equal(a, b) for a, b in zip(got, want)), chains
+        m.graph_chains = None
+        for opt, val in (("small", 2), ("pw_ws", 1), ("dw_persist", 2), ("dw_nstage", 4)):
+            _lib.set_option(opt, val)
+            m.invalidate_graphs()
+            got = m.predict_ids(x)
+            _lib.set_option(opt, {"small": 0, "pw_ws": 0, "dw_persist": 1, "dw_nstage": 0}[opt])
+            assert all(torch.equal(a, b) for a, b in zip(got, want)), opt
+    finally:
+        m.graph_chains = None
+        for opt, val in (("small", 0), ("pw_ws", 0), ("dw_persist", 1), ("dw_nstage", 0)):
+            _lib.set_option(opt, val)
+
+
 def test_batch_independence():
     """tests/utils.py:70-97 analogue for inference: utterance b's logits do not depend on the other rows."""
     m, _ = build_qn5x5()
