@@ -424,9 +424,11 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __fl
 __device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(v); }
 
 constexpr int NORM_WARPS = 8;
-constexpr int NORM_REG = 64;  // values per lane kept in registers => F <= 2048 single pass
+constexpr int NORM_REG = 64;  // most values per lane kept in registers => F <= 2048 single pass
 
-template <typename OutT>
+// REG = values per lane held in registers (instantiated for 8 / 16 / 24 / 32 / 48 / 64: the launcher picks the smallest
+// that covers max(F, out_pitch), so a 751-frame row costs 24 predicated iterations per pass instead of 64)
+template <typename OutT, int REG>
 __global__ void __launch_bounds__(NORM_WARPS * 32)
 normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restrict__ lengths, int rows,
                       int nfilt, int F, int hop, float div_guard, OutT* __restrict__ out, int out_pitch,
@@ -444,11 +446,11 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
   const float* in = logmel + (size_t)row * F;
   OutT* o = out + (size_t)row * out_pitch;
 
-  if (F <= NORM_REG * 32) {
-    float v[NORM_REG];
+  if (F <= REG * 32 && out_pitch <= REG * 32) {
+    float v[REG];
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < NORM_REG; ++j) {
+    for (int j = 0; j < REG; ++j) {
       const int t = lane + 32 * j;
       v[j] = (t < n) ? in[t] : 0.f;
       s += (double)v[j];
@@ -457,7 +459,7 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
     const float mean = (float)(s / (double)n);
     double ss = 0.0;
 #pragma unroll
-    for (int j = 0; j < NORM_REG; ++j) {
+    for (int j = 0; j < REG; ++j) {
       const int t = lane + 32 * j;
       const float d = (t < n) ? (v[j] - mean) : 0.f;
       ss += (double)d * (double)d;
@@ -468,7 +470,7 @@ normalize_rows_kernel(const float* __restrict__ logmel, const int64_t* __restric
     const float stdv = (float)sqrt(ss / (double)n);
     const float den = stdv + div_guard;
 #pragma unroll
-    for (int j = 0; j < NORM_REG; ++j) {
+    for (int j = 0; j < REG; ++j) {
       const int t = lane + 32 * j;
       if (t < out_pitch) store_out(o + t, (t < n) ? (v[j] - mean) / den : 0.f);
     }
@@ -642,16 +644,24 @@ extern "C" int ts_feature_normalize(const float* logmel, const int64_t* lengths,
              "ts_feature_normalize: bad dtype %d", out_dtype);
   const int rows = B * nfilt;
   const int grid = ceil_div(rows, feat::NORM_WARPS);
-  if (out_dtype == TS_F32) {
-    feat::normalize_rows_kernel<float><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        logmel, lengths, rows, nfilt, F, hop, div_guard, (float*)out, out_pitch, seq_len_out);
-  } else if (out_dtype == TS_F16) {
-    feat::normalize_rows_kernel<__half><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        logmel, lengths, rows, nfilt, F, hop, div_guard, (__half*)out, out_pitch, seq_len_out);
-  } else {
-    feat::normalize_rows_kernel<__nv_bfloat16><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        logmel, lengths, rows, nfilt, F, hop, div_guard, (__nv_bfloat16*)out, out_pitch, seq_len_out);
-  }
+  const int need = ceil_div(F > out_pitch ? F : out_pitch, 32);   // values per lane
+#define TS_NORM_LAUNCH(T, REG)                                                                                     \
+  feat::normalize_rows_kernel<T, REG><<<grid, feat::NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(                  \
+      logmel, lengths, rows, nfilt, F, hop, div_guard, (T*)out, out_pitch, seq_len_out)
+#define TS_NORM_DISPATCH(T)                       \
+  do {                                            \
+    if (need <= 8) TS_NORM_LAUNCH(T, 8);          \
+    else if (need <= 16) TS_NORM_LAUNCH(T, 16);   \
+    else if (need <= 24) TS_NORM_LAUNCH(T, 24);   \
+    else if (need <= 32) TS_NORM_LAUNCH(T, 32);   \
+    else if (need <= 48) TS_NORM_LAUNCH(T, 48);   \
+    else TS_NORM_LAUNCH(T, 64);                   \
+  } while (0)
+  if (out_dtype == TS_F32) TS_NORM_DISPATCH(float);
+  else if (out_dtype == TS_F16) TS_NORM_DISPATCH(__half);
+  else TS_NORM_DISPATCH(__nv_bfloat16);
+#undef TS_NORM_DISPATCH
+#undef TS_NORM_LAUNCH
   TS_LAUNCH_CHECK("normalize_rows_kernel");
   return TS_OK;
 }
