@@ -119,6 +119,14 @@ dw_persist_kernel(const __grid_constant__ Params p) {
     tl = (int)(g - (long long)c * p.tiles_per_chan);
   };
   const uint32_t box_bytes = (uint32_t)(128 * p.R * p.NB);
+  // the FIRST channel's taps are on the critical path of the whole CTA (its Toeplitz blocks gate the first MMA): issue their
+  // global loads before anything else so that their latency hides under the prologue (one tap per builder thread, K <= 192)
+  float tap0 = 0.f;
+  if (tid >= 64 && tid - 64 < p.K && ntiles > 0) {
+    int c0, t0;
+    item(0, c0, t0);
+    tap0 = __ldg(p.w + (size_t)c0 * p.K + (tid - 64));
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.in);
@@ -217,11 +225,15 @@ dw_persist_kernel(const __grid_constant__ Params p) {
     // (the epilogue warps have nothing to do yet); afterwards warps 2-3 alone build one channel ahead of the tensor core.
     const int OFF = 64 * p.HL + 63 - p.P;
     const int span = 64 * p.NQ + 70;
-    auto build = [&](int c, int buf, int bt, int nthr, int bar_id) {
+    auto build = [&](int c, int buf, int bt, int nthr, int bar_id, bool first) {
       named_bar_sync(bar_id, nthr);   // every builder is done reading the previous tap line
       for (int i = bt; i < span; i += nthr) wp[i] = 0.f;
       named_bar_sync(bar_id, nthr);
-      for (int k = bt; k < p.K; k += nthr) wp[OFF + k * p.D] = __ldg(p.w + (size_t)c * p.K + k);
+      if (first && p.K <= THREADS - 64) {   // preloaded at kernel entry (bt == tid - 64 for the first build)
+        if (bt < p.K) wp[OFF + bt * p.D] = tap0;
+      } else {
+        for (int k = bt; k < p.K; k += nthr) wp[OFF + k * p.D] = __ldg(p.w + (size_t)c * p.K + k);
+      }
       named_bar_sync(bar_id, nthr);
       uint8_t* dst = sB + buf * p.NQ * BQ;
       for (int ci = bt; ci < p.NQ * 64 * 8; ci += nthr) {
@@ -236,7 +248,7 @@ dw_persist_kernel(const __grid_constant__ Params p) {
     };
     int cur_c, tl0;
     item(0, cur_c, tl0);
-    build(cur_c, 0, tid - 64, THREADS - 64, 3);
+    build(cur_c, 0, tid - 64, THREADS - 64, 3, true);
     named_bar_sync(3, THREADS - 64);   // all 192 threads' writes are fenced before the 64 arrivals complete the phase
     if (warp < 4) {
       ptx::mbar_arrive(&b_ready[0]);
@@ -248,7 +260,7 @@ dw_persist_kernel(const __grid_constant__ Params p) {
         cur_c = c;
         ++j;
         ptx::mbar_wait(&b_free[j % p.nbuf], ((j / p.nbuf) & 1) ^ 1);   // the MMAs that read this buffer have retired
-        build(c, j % p.nbuf, tid - 64, BUILDERS, 2);
+        build(c, j % p.nbuf, tid - 64, BUILDERS, 2, false);
         ptx::mbar_arrive(&b_ready[j % p.nbuf]);
       }
     }
