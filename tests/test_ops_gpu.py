@@ -297,3 +297,26 @@ def test_ctc_greedy_known_answers(golden_decode):
     rows = to_rows(logits)
     ids3, _, _ = ops.ctc_greedy(rows, T, -1)
     assert np.array_equal(ids3.cpu().numpy(), idx)
+    # word-piece vocabularies (V >= 128: rows split over the warps of a CTA, partial results merged): torch.argmax's rules
+    # survive the merge -- the FIRST maximal index wins across slices, the first NaN beats everything, -inf columns give 0
+    for V2, T2 in ((1025, 251), (128, 33), (300, 97)):
+        lw = rng.standard_normal((3, V2, T2)).astype(np.float32)
+        lw[0, :, 5] = -np.inf                                   # all -inf -> index 0
+        lw[0, [7, 8, 600 % V2, V2 - 1], 6] = 9.0                # four-way tie across different warps' slices -> 7
+        lw[1, [V2 - 1, 3], 0] = [np.nan, np.nan]                # two NaNs -> the first one (3)
+        lw[1, 100, 1] = np.nan; lw[1, 17, 1] = 50.0             # NaN beats a larger finite value
+        lw[2, :, :] = np.round(lw[2] * 2) / 2                   # many exact ties
+        want = np.empty((3, T2), np.int64)
+        for b_ in range(3):
+            for t_ in range(T2):
+                col_ = lw[b_, :, t_]
+                nn = np.nonzero(np.isnan(col_))[0]
+                want[b_, t_] = nn[0] if nn.size else int(np.argmax(col_))
+        got = ops.ctc_greedy(dev(lw), T2, -1)[0].cpu().numpy()
+        assert np.array_equal(got, want), (V2, T2)
+        assert np.array_equal(got, torch.from_numpy(lw).argmax(1).numpy())       # torch agrees (NaN maximal, first index)
+        lb = torch.from_numpy(lw).cuda().bfloat16()                                # bf16 rows, pitch > T
+        rows_w = torch.zeros((3, V2, ops.row_pitch(T2)), device="cuda", dtype=torch.bfloat16)
+        rows_w[:, :, :T2] = lb
+        gb = ops.ctc_greedy(rows_w, T2, -1)[0].cpu()
+        assert torch.equal(gb, lb.float().cpu().argmax(1))

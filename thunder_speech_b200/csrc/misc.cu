@@ -344,12 +344,74 @@ extern "C" int ts_se_fc(const void* pool, int pool_dtype, int B, int C, int H, i
   return TS_OK;
 }
 
+namespace ts {
+namespace misc {
+// Large vocabularies (Citrinet: V = 1025): one thread per frame walking all V rows is latency bound (256 dependent rounds of
+// four loads).  Here a CTA owns 32 frames and its 8 warps each take the rows v = w, w + 8, ... (32 consecutive frames per
+// load: coalesced), then the 8 partial results per frame are merged with torch.argmax's rules: the FIRST NaN wins, otherwise
+// the largest value with the SMALLEST index.
+template <typename InT>
+__global__ void __launch_bounds__(256)
+ctc_argmax_wide_kernel(const InT* __restrict__ logits, int V, int T, int pitch, int64_t* __restrict__ ids) {
+  __shared__ float s_best[8][32];
+  __shared__ int s_idx[8][32];
+  __shared__ int s_nan[8][32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + lane;
+  float best = -INFINITY;
+  int bi = -1, nan_i = INT_MAX;
+  if (t < T) {
+    const InT* base = logits + (size_t)b * V * pitch + t;
+    int v = w;
+    for (; v + 24 < V; v += 32) {   // 4 independent loads in flight per thread, 32 per frame across the warps
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = ld_as_float(base + (size_t)(v + 8 * u) * pitch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (x[u] != x[u]) nan_i = min(nan_i, v + 8 * u);
+        else if (x[u] > best || bi < 0) { best = x[u]; bi = v + 8 * u; }
+      }
+    }
+    for (; v < V; v += 8) {
+      const float x = ld_as_float(base + (size_t)v * pitch);
+      if (x != x) nan_i = min(nan_i, v);
+      else if (x > best || bi < 0) { best = x; bi = v; }
+    }
+  }
+  s_best[w][lane] = best;
+  s_idx[w][lane] = bi;
+  s_nan[w][lane] = nan_i;
+  __syncthreads();
+  if (w == 0 && t < T) {
+    float gb = s_best[0][lane];
+    int gi = s_idx[0][lane], gn = s_nan[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float vb = s_best[k][lane];
+      const int vi = s_idx[k][lane];
+      gn = min(gn, s_nan[k][lane]);
+      if (vi >= 0 && (gi < 0 || vb > gb || (vb == gb && vi < gi))) { gb = vb; gi = vi; }
+    }
+    ids[(size_t)b * T + t] = gn != INT_MAX ? gn : gi;
+  }
+}
+}  // namespace misc
+}  // namespace ts
+
 extern "C" int ts_ctc_greedy(const void* logits, int dtype, int B, int V, int T, int pitch, int64_t* ids,
                              int64_t* collapsed, int32_t* counts, int drop_blank, void* stream) {
   TS_REQUIRE(logits && ids && collapsed && counts, TS_ERR_INVALID, "ts_ctc_greedy: null pointer");
   TS_REQUIRE(B > 0 && V > 0 && T > 0 && pitch >= T && B <= 65535, TS_ERR_INVALID, "ts_ctc_greedy: bad sizes");
   dim3 grid(ceil_div(T, 128), B);
-  if (dtype == TS_F32) {
+  if (V >= 128 && (dtype == TS_F32 || dtype == TS_BF16)) {   // word-piece vocabularies: rows split over the warps of a CTA
+    dim3 gw(ceil_div(T, 32), B);
+    if (dtype == TS_F32)
+      misc::ctc_argmax_wide_kernel<float><<<gw, 256, 0, (cudaStream_t)stream>>>((const float*)logits, V, T, pitch, ids);
+    else
+      misc::ctc_argmax_wide_kernel<__nv_bfloat16><<<gw, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, V, T, pitch,
+                                                                                   ids);
+  } else if (dtype == TS_F32) {
     misc::ctc_argmax_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)logits, V, T, pitch, ids);
   } else if (dtype == TS_BF16) {
     misc::ctc_argmax_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, V, T,
