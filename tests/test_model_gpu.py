@@ -174,7 +174,7 @@ def test_experiment_knobs_do_not_change_results(model):
             got = m.predict_ids_graphed(x)
             assert all(torch.equal(a, b) for a, b in zip(got, want)), chains
         m.graph_chains = None
-        for opt, val in (("small", 2), ("pw_ws", 1), ("dw_persist", 2), ("dw_nstage", 4)):
+        for opt, val in (("small", 2), ("pw_ws", 1), ("dw_persist", 2), ("dw_nstage", 3)):
             _lib.set_option(opt, val)
             m.invalidate_graphs()
             got = m.predict_ids(x)

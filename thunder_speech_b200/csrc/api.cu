@@ -31,7 +31,7 @@ static Option g_options[] = {
     {"dw_base_offset", {0}},
     {"dw_share_halo", {1}},
     {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
-    {"dw_nstage", {0}},       // per-channel Toeplitz kernel: input stages (0 = default 3)
+    {"dw_nstage", {0}},       // per-channel Toeplitz kernel: input stages (0 = default 4)
     {"tma_l2", {3}},          // L2 promotion of every tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
     {"dwp_nbuf", {0}},        // persistent Toeplitz kernel: Toeplitz buffers (0 = auto: 2 when NQ <= 3), experiment
     {"dwp_nstage", {0}},      // ... input stages (0 = auto)

@@ -19,7 +19,10 @@ namespace dwt2 {
 constexpr int L = 64;
 constexpr int MROWS = 128;
 constexpr int A_STAGE = 17 * 1024;     // 130 rows x 128 B rounded up to a multiple of 1024
-constexpr int NSTAGE = 3;              // default input stages (option dw_nstage: 2..4, clamped to what two CTAs per SM allow)
+constexpr int NSTAGE = 4;              // default input stages (option dw_nstage: 2..4), clamped to what two CTAs per SM allow:
+                                       // 4 x 17 KB + 24 KB Toeplitz + 16 KB staging = 109 KB per CTA.  Alternating A/B on one box,
+                                       // 3 vs 4 stages: QuartzNet 256 x 15 s 11.24 -> 11.16 ms (three pairs of runs, all the same
+                                       // sign), Citrinet-1024 128 x 20 s 25.02 -> 24.86 ms
 constexpr int MAX_NSTAGE = 4;
 constexpr int BQ = 64 * 128;           // one Toeplitz block: 64 rows (r) x 64 k (j) bf16 = 8 KB
 constexpr int MAX_NQ = 5;              // Toeplitz blocks: left halo + centre + right halo windows (3 for K <= 129, dilation 1)
