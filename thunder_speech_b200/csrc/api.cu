@@ -31,6 +31,7 @@ static Option g_options[] = {
     {"dw_base_offset", {0}},
     {"dw_share_halo", {1}},
     {"dw_pro", {30}},         // per-CTA prologue of the Toeplitz kernel in tenths of a tile (grid cost model)
+    {"dw_persist_c", {592}},  // ... heuristic: persistent kernel only above this many channels (two waves of per-channel CTAs)
     {"dw_nstage", {0}},       // per-channel Toeplitz kernel: input stages (0 = default 4)
     {"tma_l2", {3}},          // L2 promotion of every tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
     {"dwp_nbuf", {0}},        // persistent Toeplitz kernel: Toeplitz buffers (0 = auto: 2 when NQ <= 3), experiment
@@ -61,6 +62,7 @@ int small_footprint(long long frames) {
   const int m = opt("small").load(std::memory_order_relaxed);
   return m >= 2 || (m == 1 && frames <= (long long)opt("small_frames").load(std::memory_order_relaxed));
 }
+int option_dw_persist_c() { return opt("dw_persist_c").load(std::memory_order_relaxed); }
 int option_dw_nstage() { return opt("dw_nstage").load(std::memory_order_relaxed); }
 int option_tma_l2() { return opt("tma_l2").load(std::memory_order_relaxed); }
 int option_dwp_nbuf() { return opt("dwp_nbuf").load(std::memory_order_relaxed); }

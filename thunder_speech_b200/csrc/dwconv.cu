@@ -186,6 +186,7 @@ int launch_dw_tma(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, con
 int launch_dw_persist(const __nv_bfloat16* x, int B, int C, int T, int pitch_in, const float* w, int K, int D, int P,
                       const int32_t* lens, __nv_bfloat16* y, int pitch_out, cudaStream_t st, int f16);
 int option_dw_persist();
+int option_dw_persist_c();
 int small_footprint(long long frames);
 }
 using namespace ts;
@@ -212,17 +213,20 @@ extern "C" int ts_dw_conv(const void* x, int B, int C, int T_in, int pitch_in, c
   // stride-1 / dilation-1 / odd-K "same" convolutions: Toeplitz MMA on the tensor cores (dwmma.cu)
   // ... through TMA when the caller guarantees rows are already zero beyond len_in (or there are no lengths)
   if (S == 1 && option_dw_mma() && option_dw_tma() && (len_in == nullptr || (flags & TS_DW_INPUT_PREMASKED))) {
-    // Persistent multi-channel CTAs (dwmma3.cu) where one CTA per (channel, tile group) cannot amortise its prologue:
-    // few tiles per channel (small per-GPU batches, short sequences) and the 5-block Toeplitz set of the dilated layer.
-    // Measured on B200 inside the full model (tools/ab_dw_persist.sh): Citrinet-1024 at 16 x 20 s 5.68 -> 5.13 ms, the
-    // K = 87 / dilation 2 layer 104 -> 90 us; QuartzNet 15x5 at 256 x 15 s (29 tiles per channel) 11.85 -> 12.25 ms, hence
-    // the threshold.  Option dw_persist: 0 = never, 1 = this heuristic, 2 = always.
+    // Persistent multi-channel CTAs (dwmma3.cu) where one CTA per (channel, tile group) cannot amortise its prologue: few
+    // tiles per channel AND more than two waves of channels (Citrinet's 1024-channel layers at small per-GPU batches / short
+    // sequences), and the 5-block Toeplitz set of the dilated layer.  Measured on B200 inside the full models
+    // (tools/ab_opts.sh "dw_persist=1" "dw_persist=0", per-channel kernel with 4 input stages): Citrinet-1024 at 16 / 32 x 20 s
+    // persistent 5.01 / 7.40 ms vs per-channel 5.48 / 7.80 ms; QuartzNet 15x5 (256 / 512 channels: one or two waves of
+    // per-channel CTAs) at 16 / 32 / 64 x 15 s per-channel 1.63 / 2.26 / 3.41 ms vs persistent 1.77 / 2.30 / 3.55 ms, and at
+    // 256 x 15 s (29 tiles per channel) 11.85 vs 12.25 ms.  Option dw_persist: 0 = never, 1 = this heuristic, 2 = always.
     {
       const int W = pitch_in / 64, HL = ceil_div(P, 64), NQ = HL + 1 + (63 + P) / 64;
       const int HR = NQ - 1 - HL, R = W + (HL > HR ? HL : HR);
       const int tiles_per_chan = R > 0 && R <= 128 ? ceil_div(B, 128 / R) : 1 << 30;
       if (option_dw_persist() >= 2 ||
-          (option_dw_persist() == 1 && (NQ > 3 || tiles_per_chan <= 8 || small_footprint((long long)B * pitch_in)))) {
+          (option_dw_persist() == 1 &&
+           (NQ > 3 || (tiles_per_chan <= 8 && C > option_dw_persist_c()) || small_footprint((long long)B * pitch_in)))) {
         const int rc = launch_dw_persist(xb, B, C, T_in, pitch_in, w, K, D, P, len_in, yb, pitch_out, st, f16);
         if (rc != TS_ERR_UNSUPPORTED) return rc;
       }
