@@ -112,6 +112,10 @@ dw_tma_kernel(const __grid_constant__ Params p) {
   // n-th tile of this CTA; reversed walks start at the last utterances (CTAs with a low blockIdx.y are scheduled first)
   auto tile_at = [&](int n) { return p.rev ? p.tiles_per_chan - 1 - (tile0 + n) : tile0 + n; };
   const uint32_t box_bytes = (uint32_t)(128 * p.R * p.NB);
+  // this channel's taps gate the Toeplitz build and with it the first MMA: their global loads are issued before anything
+  // else so that the latency hides under the prologue (one tap per builder thread; K <= 192)
+  float tap0 = 0.f;
+  if (tid >= 64 && tid - 64 < p.K) tap0 = __ldg(p.w + (size_t)c * p.K + (tid - 64));
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.in);
@@ -201,7 +205,11 @@ dw_tma_kernel(const __grid_constant__ Params p) {
     // the K taps of this channel are staged once in shared memory (borrowing the output staging buffer, which the epilogue
     // first touches only after b_ready): the build below then needs no global loads
     float* wc = reinterpret_cast<float*>(sO);
-    for (int k = tid - 64; k < p.K; k += THREADS - 64) wc[k] = __ldg(p.w + (size_t)c * p.K + k);
+    if (p.K <= THREADS - 64) {
+      if (tid - 64 < p.K) wc[tid - 64] = tap0;      // fetched at kernel entry
+    } else {
+      for (int k = tid - 64; k < p.K; k += THREADS - 64) wc[k] = __ldg(p.w + (size_t)c * p.K + k);
+    }
     named_bar_sync(2, THREADS - 64);
     const int kd = p.K * p.D;
     for (int ci = tid - 64; ci < p.NQ * 64 * 8; ci += THREADS - 64) {
